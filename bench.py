@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — MC move attempts/sec of the annealing hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference algorithm on the host cores
+
+Workload (BASELINE.json configs[1]): (H2O)_20 TIP3P, 4096 independent seeded chains per
+GPU, the shipped annealing block (10000 K, 4 teeth x 10 points x 20000 moves = 800 000 move attempts per
+chain), seed = 1000 + global chain index, initial structures from the device-side Space.propagate.
+A step = one whole annealing job over all chains: `value` times the anneal kernel with the chain state
+already resident in HBM (CUDA events on the launch stream); `e2e` times the public call sequence a host
+makes — seeds up from host memory, propagate, anneal, per-chain minima / summaries / point records and the
+winning structure back to host memory.  Under torchrun (N > 1) chains shard over ranks with no data-path
+collective; the only exchange is the final NCCL all-gather of per-chain minima, inside the e2e region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "MC move attempts/sec"
+UNIT = "moves/s"
+FLOPS_PER_PAIR = 19.0          # A = 0 for every shipped species
+CHAINS_PER_GPU = 4096
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="h2o20", choices=["sample8", "h2o20", "nh4cl32", "mixed64", "h2o256"])
+    ap.add_argument("--chains-per-gpu", type=int, default=0)
+    ap.add_argument("--moves-per-point", type=int, default=0, help="override Moves per Point (default: shipped 20000)")
+    ap.add_argument("--threads-per-chain", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def load_problem(args):
+    from helpers import workload_config
+    from transrot_b200 import Config, read_dbase, system_from_config
+
+    golden = os.path.join(ROOT, "tests", "golden")
+    dbase = read_dbase(os.path.join(golden, "shipped_species.dbase.txt"))
+    base = Config.parseConfig(os.path.join(golden, "sample8.config.txt"))
+    # timing runs: every Write* option / Static Temperature / Finale off
+    kw = dict(writeEnergiesEnabled=False, writeConfHeatCapacitiesEnabled=False, writeAcceptanceRatios=False, finale=False,
+              staticTemp=False)
+    if args.moves_per_point > 0:
+        kw["movePerPt"] = args.moves_per_point
+    cfg = workload_config(base, args.workload, **kw)
+    return dbase, cfg, system_from_config(dbase, cfg)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+
+def cpu_port_rate(dbase, cfg, seconds: float, first_seed: int = 1000):
+    """The oracle (C restatement of the reference algorithm) on every host core: one chain per thread
+    (ctypes releases the GIL), each a bounded sample of the same workload.  Returns (moves/s, cores, sample)."""
+    from oracle.oracle import oracle_from_config
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # calibrate one core on a tiny slice, then size the sample to ~`seconds`
+    probe = cfg.copy(movePerPt=200, ptsPerTooth=2, numTeeth=1)
+    sp = oracle_from_config(dbase, probe, first_seed)
+    t0 = time.perf_counter()
+    sp.sawtooth_anneal(sp.calc_energy())
+    per_move = (time.perf_counter() - t0) / probe.total_moves()
+    pts = cfg.num_points()
+    mpp = max(1, min(cfg.movePerPt, int(seconds / per_move / pts)))
+    sample_cfg = cfg.copy(movePerPt=mpp)
+    spaces = []
+    for i in range(cores):
+        s = oracle_from_config(dbase, sample_cfg, first_seed + i)
+        spaces.append((s, s.calc_energy()))
+    done = [0] * cores
+
+    def work(i):
+        s, e0 = spaces[i]
+        done[i] = s.sawtooth_anneal(e0).moves
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    sample = (f"{cores} chains (one per core), full sawtooth schedule with Moves per Point = {mpp} "
+              f"({sample_cfg.total_moves()} moves per chain), {dt:.1f} s wall")
+    return sum(done) / dt, cores, sample, dt
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU algorithm for the path, timed on the host cores.  No JVM exists in
+    this image or on the GPU box and /root/reference does not travel, so this is the oracle port
+    (kind = "port": a C restatement, faster than the JVM original - a conservative baseline)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dbase, cfg, system = load_problem(args)
+    rates, secs = [], []
+    sample = ""
+    cores = 1
+    per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        r, cores, sample, dt = cpu_port_rate(dbase, cfg, per_step, first_seed=1000)
+        if i >= args.warmup:
+            rates.append(r)
+            secs.append(dt)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_descr(args, cfg, system, CHAINS_PER_GPU if not args.chains_per_gpu else args.chains_per_gpu),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = the upper half of the samples (the sampler also sees the untimed gaps)
+        s = sorted(sm)
+        return {"sm_mhz": float(np.median(s[len(s) // 2:])), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def workload_descr(args, cfg, system, chains_per_gpu):
+    return {
+        "workload": f"{args.workload}: {system.n_mol} particles / {system.n_sites} sites, {chains_per_gpu} independent seeded "
+                    f"chains per GPU, sawtooth anneal {cfg.maxTemp:g} K, {cfg.numTeeth} teeth x {cfg.ptsPerTooth} points x "
+                    f"{cfg.movePerPt} moves ({cfg.total_moves()} move attempts per chain)",
+        "chains_per_gpu": chains_per_gpu,
+        "moves_per_chain": cfg.total_moves(),
+        "pair_evals_per_move_ref": system.pair_evals_per_move(),
+        "seed_rule": "1000 + global chain index",
+        "l2": "flushed between timed steps (256 MiB write); chain state (RNG 30 MB + records) is rewritten by the untimed init",
+        "parallelism": f"chains sharded over {args.gpus} GPU(s), no data-path collective; final NCCL all-gather of minima",
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from transrot_b200 import Engine, MINIMUM_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this backend has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dbase, cfg, system = load_problem(args)
+    cpg = args.chains_per_gpu or (CHAINS_PER_GPU if args.workload != "h2o256" else 2 * 148)
+    first = rank * cpg
+    seeds = np.arange(1000 + first, 1000 + first + cpg, dtype=np.int64)
+    pinned_seeds = torch.from_numpy(seeds).pin_memory()
+
+    eng = Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_system(system)
+    eng.set_schedules(cfg)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    minima_dev = torch.empty(cpg * MINIMUM_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    gathered = torch.empty(world * cpg * MINIMUM_DTYPE.itemsize, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def init(record):
+        eng.set_options(trace_moves=0, record_points=record, record_snapshots=record, threads_per_chain=args.threads_per_chain)
+        eng.init_chains_seeded(pinned_seeds.numpy(), cfg.spaceLen, cfg.maxPropFailures, first_chain=first)
+
+    # FP64 peak of this device, measured live (not in MEASURED_PEAKS.json): the roofline denominator
+    peak_tflops, peak_clock = eng.measure_fp64_peak()
+
+    # ---- value: the anneal kernel, chain state resident in HBM
+    def device_step():
+        init(False)
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        e0.record(stream)
+        eng.run(0)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), eng.last_run_ms(), eng.launch_count() - l0
+
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, ms_kernel, launches = 0.0, 0.0, 0
+    for _ in range(args.steps):
+        a, b, c = device_step()
+        ms_dev += a
+        ms_kernel += b
+        launches += c
+    summ = eng.summary()
+    assert int(summ["done"].sum()) == cpg, "not every chain finished"
+    moves = int(summ["moves"].sum())
+    pair_evals = int(summ["pair_evals"].sum())
+
+    # ---- e2e: the host-facing call sequence, host buffers in and out
+    h2d = seeds.nbytes
+    d2h_holder = {}
+
+    def e2e_step():
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        init(True)                                   # H2D seeds (+ propagate on the device)
+        eng.run(0)
+        eng.pack_minima_device(minima_dev.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, minima_dev)
+            allmin = gathered.cpu().numpy().view(MINIMUM_DTYPE)
+        else:
+            allmin = minima_dev.cpu().numpy().view(MINIMUM_DTYPE)
+        s = eng.summary()
+        pts = eng.points()
+        se, st, _ = eng.snapshots(with_sites=False)
+        best = int(np.argmin(allmin["energy"]))
+        nbytes = allmin.nbytes + s.nbytes + pts.nbytes + se.nbytes + st.nbytes
+        if first <= int(allmin["chain"][best]) < first + cpg:       # the owner fetches the winning structure
+            x, e, t = eng.min_structure(int(allmin["chain"][best]) - first)
+            nbytes += x.nbytes
+        torch.cuda.synchronize()
+        d2h_holder["n"] = nbytes
+        d2h_holder["best"] = (float(allmin["energy"][best]), int(allmin["chain"][best]), int(allmin["tooth"][best]))
+        return (time.perf_counter() - t0) * 1e3
+
+    e2e_step()   # one warm-up of the host path (allocations, pinned staging)
+    ms_e2e = 0.0
+    for _ in range(args.steps):
+        ms_e2e += e2e_step()
+    clocks = sampler.stop()
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_kernel, ms_e2e], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([moves, pair_evals, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_dev, ms_kernel, ms_e2e = [float(v) for v in t.cpu()]
+    moves_all, pairs_all, launches_all = [float(v) for v in tot.cpu()]
+    steps = args.steps
+    value = moves_all * steps / (ms_dev * 1e-3)
+    e2e_value = moves_all * steps / (ms_e2e * 1e-3)
+    # roofline of the dominant kernel (anneal_kernel): executed pair evaluations x 19 flops over its device time, per GPU
+    achieved_tflops = (pairs_all / world) * steps * FLOPS_PER_PAIR / (ms_kernel * 1e-3) / 1e12
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_descr(args, cfg, system, cpg),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_holder["n"]),
+                    "ms_per_step": ms_e2e / steps},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved_tflops / peak_tflops, "traffic": None,
+                "kernel": "anneal_kernel", "flops_per_pair_eval": FLOPS_PER_PAIR,
+                "pair_evals_per_launch": pairs_all / world,
+                "peak_source": f"DFMA micro-benchmark run live on this device (tr_measure_fp64_peak), implied SM clock {peak_clock:.0f} MHz; "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "ms_per_launch": ms_kernel / steps,
+            },
+            "best_minimum": {"energy": d2h_holder["best"][0], "chain": d2h_holder["best"][1], "tooth": d2h_holder["best"][2]},
+        }
+        if not args.no_cpu_baseline:
+            r, cores, sample, _ = cpu_port_rate(dbase, cfg, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -98,6 +98,7 @@ class AnnealOut(C.Structure):
         ("points", C.c_void_p), ("points_cap", C.c_int64), ("points_len", C.c_int64),
         ("snap_tooth", C.c_void_p), ("snap_energy", C.c_void_p), ("snap_coords", C.c_void_p),
         ("snap_cap", C.c_int64), ("snap_len", C.c_int64),
+        ("trace_abs", C.c_void_p),
         ("moves", C.c_int64), ("evaluated", C.c_int64), ("pair_evals", C.c_int64),
     ]
 
@@ -210,6 +211,7 @@ class AnnealResult:
         self.snap_tooth = np.zeros(0, dtype=np.int32)
         self.snap_energy = np.zeros(0, dtype=np.float64)
         self.snap_coords = np.zeros((0, 0, 3), dtype=np.float64)
+        self.trace_abs = np.zeros(0, dtype=np.float64)
         self.moves = 0
         self.evaluated = 0
         self.pair_evals = 0
@@ -382,6 +384,7 @@ class OracleSpace:
         S = self.n_sites
         res = AnnealResult()
         trace = np.zeros(max(trace_cap, 1), dtype=TRACE_DTYPE)
+        trace_abs = np.zeros(max(trace_cap, 1), dtype=np.float64)
         points = np.zeros(max(points_cap, 1), dtype=POINT_DTYPE)
         st = np.zeros(max(snap_cap, 1), dtype=np.int32)
         se = np.zeros(max(snap_cap, 1), dtype=np.float64)
@@ -390,9 +393,11 @@ class OracleSpace:
             trace=trace.ctypes.data if trace_cap else None, trace_cap=trace_cap,
             points=points.ctypes.data if points_cap else None, points_cap=points_cap,
             snap_tooth=st.ctypes.data, snap_energy=se.ctypes.data, snap_coords=sc.ctypes.data, snap_cap=snap_cap,
+            trace_abs=trace_abs.ctypes.data,
         )
         res.final_energy = float(self.L.or_sawtooth_anneal(self.h, float(starting_energy), C.byref(out)))
         res.trace = trace[: out.trace_len].copy()
+        res.trace_abs = trace_abs[: out.trace_len].copy()
         res.points = points[: out.points_len].copy()
         res.snap_tooth = st[: out.snap_len].copy()
         res.snap_energy = se[: out.snap_len].copy()

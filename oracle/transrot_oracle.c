@@ -159,6 +159,7 @@ struct or_space {
     or_config cfg;
     double minEnergy; int minEnergyToothNum;   /* Space.java:23-24 */
     int64_t pair_evals;
+    double abs_acc;    /* test aid: running sum of |pair term| */
 };
 
 static void atom_reset_temps(atom *a) { a->tempx = a->x; a->tempy = a->y; a->tempz = a->z; } /* Atom.java:121 */
@@ -350,7 +351,9 @@ static inline double atom_energy_at(or_space *s, const atom *self, double sx, do
     double A = v[0], B = v[1], C = v[2], D = v[3];
     double r = sqrt(java_pow(other->x - sx, 2) + java_pow(other->y - sy, 2) + java_pow(other->z - sz, 2));
     s->pair_evals++;
-    return (self->kTimesQ * other->q / r) + A * exp(-1 * B * r) - (C / java_pow(r, 6)) + (D / java_pow(r, 12));
+    double e = (self->kTimesQ * other->q / r) + A * exp(-1 * B * r) - (C / java_pow(r, 6)) + (D / java_pow(r, 12));
+    s->abs_acc += fabs(e);
+    return e;
 }
 
 static double mol_calc_energy(or_space *s, const molecule *m, const molecule *n)   /* Molecule.java:99-107 */
@@ -704,6 +707,7 @@ double or_sawtooth_anneal(or_space *s, double startingEnergy, or_anneal_out *out
                 int acc;
                 int magwalk;
                 int64_t pe = s->pair_evals;
+                s->abs_acc = 0.0;
                 if (or_mt_next_double(&s->rM) >= 0.5 && m->natoms > 1) {
                     if (or_mt_next_double(&s->rM) >= magwalkProbRot) {
                         magwalk = 0;
@@ -733,6 +737,7 @@ double or_sawtooth_anneal(or_space *s, double startingEnergy, or_anneal_out *out
                 if (out->trace && out->trace_len < out->trace_cap) {
                     rec.magwalk = (int8_t)magwalk;
                     rec.running = startingEnergy;
+                    if (out->trace_abs) out->trace_abs[out->trace_len] = s->abs_acc;
                     out->trace[out->trace_len++] = rec;
                 }
             }

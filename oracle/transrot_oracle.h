@@ -153,6 +153,8 @@ typedef struct or_anneal_out {
     or_point_rec *points;  int64_t points_cap;  int64_t points_len;
     int32_t *snap_tooth;   double *snap_energy; double *snap_coords;
     int64_t snap_cap;      int64_t snap_len;
+    double *trace_abs;     /* [trace_cap] or NULL: sum of |pair term| over the eStart and eEnd loops of each move,
+                              the conditioning scale for comparing eStart/eEnd/dE (test aid, not in the reference) */
     int64_t moves;         /* iterations of the z-loop                     */
     int64_t evaluated;     /* moves that reached the energy loop           */
     int64_t pair_evals;    /* Atom.calcEnergy + calcTempEnergy calls made  */

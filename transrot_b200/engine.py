@@ -1,0 +1,335 @@
+"""ctypes binding of include/transrot_b200.h — the same calls the Java host would bind with Panama
+(INTEGRATION.md).  Thin by design: every number on the hot path is produced by the CUDA library.
+There is no CPU fallback; a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .host import Config, System, TransRotError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtransrot_b200.so")
+
+TR_MAX_MOL_SITES = 16
+
+
+class TrSystem(C.Structure):
+    _fields_ = [
+        ("n_mol", C.c_int32), ("n_sites", C.c_int32), ("n_types", C.c_int32), ("n_moveable", C.c_int32),
+        ("mol_site_off", C.c_void_p), ("mol_radius", C.c_void_p), ("site_type", C.c_void_p), ("site_q", C.c_void_p),
+        ("site_def", C.c_void_p), ("site_mass", C.c_void_p), ("site_ghost", C.c_void_p), ("moveable_idx", C.c_void_p),
+        ("pair_abcd", C.c_void_p),
+    ]
+
+
+SCHEDULE_DTYPE = np.dtype(
+    [
+        ("max_temp", "<f8"), ("temp_decrease_per_tooth", "<f8"), ("max_trans", "<f8"), ("magwalk_factor_trans", "<f8"),
+        ("magwalk_prob_trans", "<f8"), ("max_rot", "<f8"), ("magwalk_prob_rot", "<f8"),
+        ("moves_per_point", "<i4"), ("points_per_tooth", "<i4"), ("points_added_per_tooth", "<i4"), ("num_teeth", "<i4"),
+        ("eq_configs", "<i4"), ("finale", "<i4"), ("static_temp", "<i4"), ("write_conf_heat_capacities", "<i4"),
+    ],
+    align=True,
+)
+POINT_DTYPE = np.dtype(
+    [
+        ("tooth", "<i4"), ("point", "<i4"), ("accepted", "<i4"), ("total", "<i4"), ("movie_written", "<i4"), ("finale", "<i4"),
+        ("temp", "<f8"), ("total_energy", "<f8"), ("total_squared_energy", "<f8"), ("movie_energy", "<f8"),
+    ],
+    align=True,
+)
+TRACE_DTYPE = np.dtype(
+    [
+        ("mol", "<i4"), ("kind", "i1"), ("magwalk", "i1"), ("bounds", "i1"), ("accepted", "i1"), ("axis", "<i4"),
+        ("drew_rand", "<i4"), ("e_start", "<f8"), ("e_end", "<f8"), ("dE", "<f8"), ("rand", "<f8"), ("temp", "<f8"),
+        ("running", "<f8"),
+    ],
+    align=True,
+)
+SUMMARY_DTYPE = np.dtype(
+    [
+        ("start_energy", "<f8"), ("running_energy", "<f8"), ("min_energy", "<f8"), ("space_len", "<f8"),
+        ("moves", "<i8"), ("evaluated", "<i8"), ("accepted", "<i8"), ("pair_evals", "<i8"),
+        ("min_tooth", "<i4"), ("snapshots", "<i4"), ("points", "<i4"), ("done", "<i4"), ("prop_retries", "<i4"), ("pad_", "<i4"),
+    ],
+    align=True,
+)
+MINIMUM_DTYPE = np.dtype([("energy", "<f8"), ("chain", "<i8"), ("tooth", "<i4"), ("pad_", "<i4")], align=True)
+assert SCHEDULE_DTYPE.itemsize == 88 and POINT_DTYPE.itemsize == 56 and TRACE_DTYPE.itemsize == 64
+assert SUMMARY_DTYPE.itemsize == 88 and MINIMUM_DTYPE.itemsize == 24
+
+_SIGNATURES = {
+    "tr_create": [C.c_int, C.POINTER(C.c_void_p)],
+    "tr_destroy": [C.c_void_p],
+    "tr_last_error": [C.c_void_p],
+    "tr_set_stream": [C.c_void_p, C.c_void_p],
+    "tr_synchronize": [C.c_void_p],
+    "tr_set_system": [C.c_void_p, C.POINTER(TrSystem)],
+    "tr_set_schedules": [C.c_void_p, C.c_void_p, C.c_int32],
+    "tr_set_options": [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32],
+    "tr_init_chains_seeded": [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_int32],
+    "tr_init_chains_explicit": [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double],
+    "tr_run": [C.c_void_p, C.c_int64],
+    "tr_last_run_ms": [C.c_void_p, C.POINTER(C.c_float)],
+    "tr_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],
+    "tr_get_summary": [C.c_void_p, C.c_void_p],
+    "tr_get_sites": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "tr_get_points": [C.c_void_p, C.c_void_p, C.c_int64],
+    "tr_get_snapshots": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64],
+    "tr_get_trace": [C.c_void_p, C.c_void_p],
+    "tr_get_rng_state": [C.c_void_p, C.c_void_p],
+    "tr_pack_minima": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "tr_get_min_structure": [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)],
+    "tr_max_points": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    "tr_total_energy": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+    "tr_delta_energy": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
+    "tr_rng_words": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p],
+    "tr_measure_fp64_peak": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libtransrot_b200.so.  Raises if it was not built: nothing here can run without it."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TransRotError(
+            f"Error: {LIB_PATH} is missing; build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    for name, args in _SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = None if name == "tr_destroy" else (C.c_char_p if name == "tr_last_error" else C.c_int)
+    _lib = L
+    return L
+
+
+def schedule_from_config(cfg: Config) -> np.ndarray:
+    """The Config fields Main.sawtoothAnneal reads (Config.java:12-33) as one tr_schedule."""
+    s = np.zeros(1, dtype=SCHEDULE_DTYPE)
+    s["max_temp"] = cfg.maxTemp
+    s["temp_decrease_per_tooth"] = cfg.tempDecreasePerTooth
+    s["max_trans"] = cfg.maxTrans
+    s["magwalk_factor_trans"] = cfg.magwalkFactorTrans
+    s["magwalk_prob_trans"] = cfg.magwalkProbTrans
+    s["max_rot"] = cfg.maxRot
+    s["magwalk_prob_rot"] = cfg.magwalkProbRot
+    s["moves_per_point"] = cfg.movePerPt
+    s["points_per_tooth"] = cfg.ptsPerTooth
+    s["points_added_per_tooth"] = cfg.ptsAddedPerTooth
+    s["num_teeth"] = cfg.numTeeth
+    s["eq_configs"] = cfg.eqConfigs
+    s["finale"] = int(cfg.finale)
+    s["static_temp"] = int(cfg.staticTemp)
+    s["write_conf_heat_capacities"] = int(cfg.writeConfHeatCapacitiesEnabled)
+    return s
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Engine:
+    """One tr_ctx: one CUDA device, one batch of chains."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.tr_create(int(device), C.byref(h))
+        if rc != 0:
+            raise TransRotError((self.L.tr_last_error(None) or b"").decode() or f"tr_create failed ({rc})")
+        self.h = h
+        self.system: Optional[System] = None
+        self.n_chains = 0
+        self.trace_moves = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise TransRotError((self.L.tr_last_error(self.h) or b"").decode() or f"error {rc}")
+
+    # ---- problem definition
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.L.tr_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.L.tr_synchronize(self.h))
+
+    def set_system(self, system: System):
+        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        arrs = dict(
+            mol_site_off=c(system.mol_site_off, np.int32), mol_radius=c(system.mol_radius, np.float64),
+            site_type=c(system.site_type, np.int32), site_q=c(system.site_q, np.float64),
+            site_def=c(system.site_def, np.float64), site_mass=c(system.site_mass, np.float64),
+            site_ghost=c(system.site_ghost, np.int32), moveable_idx=c(system.moveable_idx, np.int32),
+            pair_abcd=c(system.pair_table, np.float64),
+        )
+        ts = TrSystem(n_mol=system.n_mol, n_sites=system.n_sites, n_types=system.n_types, n_moveable=len(system.moveable_idx),
+                      **{k: v.ctypes.data for k, v in arrs.items()})
+        self._ck(self.L.tr_set_system(self.h, C.byref(ts)))
+        self.system = system
+        self.n_chains = 0
+
+    def set_schedules(self, schedules):
+        """schedules: a Config, a sequence of Configs, or a SCHEDULE_DTYPE array."""
+        if isinstance(schedules, Config):
+            arr = schedule_from_config(schedules)
+        elif isinstance(schedules, np.ndarray):
+            arr = np.ascontiguousarray(schedules, dtype=SCHEDULE_DTYPE)
+        else:
+            arr = np.concatenate([schedule_from_config(c) for c in schedules])
+        self.schedules = arr
+        self._ck(self.L.tr_set_schedules(self.h, arr.ctypes.data, len(arr)))
+        self.n_chains = 0
+
+    def set_options(self, trace_moves: int = 0, record_points: bool = True, record_snapshots: bool = True, threads_per_chain: int = 0):
+        self._ck(self.L.tr_set_options(self.h, int(trace_moves), int(record_points), int(record_snapshots), int(threads_per_chain)))
+        self.trace_moves = int(trace_moves)
+
+    def init_chains_seeded(self, seeds: Sequence[int], space_len: float, max_prop_failures: int,
+                           sched_idx: Optional[Sequence[int]] = None, first_chain: int = 0):
+        s = np.ascontiguousarray(seeds, dtype=np.int64)
+        idx = None if sched_idx is None else np.ascontiguousarray(sched_idx, dtype=np.int32)
+        self._ck(self.L.tr_init_chains_seeded(self.h, len(s), int(first_chain), s.ctypes.data, _ptr(idx), float(space_len), int(max_prop_failures)))
+        self.n_chains = len(s)
+
+    def init_chains_explicit(self, n_chains: int, sites: np.ndarray, space_len: float, seeds: Optional[Sequence[int]] = None,
+                             mt_state: Optional[np.ndarray] = None, sched_idx: Optional[Sequence[int]] = None, first_chain: int = 0):
+        S = self.system.n_sites
+        x = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, S, 3)
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.int64)
+        st = None if mt_state is None else np.ascontiguousarray(mt_state, dtype=np.uint32).reshape(n_chains, 3, 625)
+        idx = None if sched_idx is None else np.ascontiguousarray(sched_idx, dtype=np.int32)
+        self._ck(self.L.tr_init_chains_explicit(self.h, int(n_chains), int(first_chain), x.ctypes.data, x.shape[0], _ptr(sd), _ptr(st), _ptr(idx), float(space_len)))
+        self.n_chains = int(n_chains)
+
+    # ---- hot path
+    def run(self, max_moves: int = 0):
+        self._ck(self.L.tr_run(self.h, int(max_moves)))
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self.L.tr_last_run_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._ck(self.L.tr_launch_count(self.h, C.byref(n)))
+        return int(n.value)
+
+    # ---- results
+    def summary(self) -> np.ndarray:
+        out = np.zeros(self.n_chains, dtype=SUMMARY_DTYPE)
+        self._ck(self.L.tr_get_summary(self.h, out.ctypes.data))
+        return out
+
+    def sites(self, with_com: bool = True):
+        S, N = self.system.n_sites, self.system.n_mol
+        x = np.zeros((self.n_chains, S, 3), dtype=np.float64)
+        com = np.zeros((self.n_chains, N, 3), dtype=np.float64) if with_com else None
+        self._ck(self.L.tr_get_sites(self.h, x.ctypes.data, _ptr(com)))
+        return x, com
+
+    def max_points(self):
+        p, s = C.c_int64(), C.c_int64()
+        self._ck(self.L.tr_max_points(self.h, C.byref(p), C.byref(s)))
+        return int(p.value), int(s.value)
+
+    def points(self) -> np.ndarray:
+        cap, _ = self.max_points()
+        out = np.zeros((self.n_chains, cap), dtype=POINT_DTYPE)
+        self._ck(self.L.tr_get_points(self.h, out.ctypes.data, cap))
+        return out
+
+    def snapshots(self, with_sites: bool = True):
+        _, cap = self.max_points()
+        e = np.zeros((self.n_chains, cap), dtype=np.float64)
+        t = np.zeros((self.n_chains, cap), dtype=np.int32)
+        x = np.zeros((self.n_chains, cap, self.system.n_sites, 3), dtype=np.float64) if with_sites else None
+        self._ck(self.L.tr_get_snapshots(self.h, e.ctypes.data, t.ctypes.data, _ptr(x), cap))
+        return e, t, x
+
+    def trace(self) -> np.ndarray:
+        out = np.zeros((self.n_chains, self.trace_moves), dtype=TRACE_DTYPE)
+        self._ck(self.L.tr_get_trace(self.h, out.ctypes.data))
+        return out
+
+    def rng_state(self) -> np.ndarray:
+        out = np.zeros((self.n_chains, 3, 625), dtype=np.uint32)
+        self._ck(self.L.tr_get_rng_state(self.h, out.ctypes.data))
+        return out
+
+    def pack_minima(self, device_ptr: int = 0) -> np.ndarray:
+        out = np.zeros(self.n_chains, dtype=MINIMUM_DTYPE)
+        self._ck(self.L.tr_pack_minima(self.h, out.ctypes.data, C.c_void_p(device_ptr) if device_ptr else None))
+        return out
+
+    def pack_minima_device(self, device_ptr: int):
+        self._ck(self.L.tr_pack_minima(self.h, None, C.c_void_p(device_ptr)))
+
+    def min_structure(self, chain: int):
+        x = np.zeros((self.system.n_sites, 3), dtype=np.float64)
+        e, t = C.c_double(), C.c_int32()
+        self._ck(self.L.tr_get_min_structure(self.h, int(chain), x.ctypes.data, C.byref(e), C.byref(t)))
+        return x, float(e.value), int(t.value)
+
+    # ---- probes
+    def total_energy(self, sites: np.ndarray) -> np.ndarray:
+        S = self.system.n_sites
+        x = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, S, 3)
+        out = np.zeros(x.shape[0], dtype=np.float64)
+        self._ck(self.L.tr_total_energy(self.h, x.ctypes.data, x.shape[0], out.ctypes.data))
+        return out
+
+    def delta_energy(self, sites: np.ndarray, mol: Sequence[int], trial: np.ndarray):
+        """trial: [n, n_sites_of_mol_max<=16, 3] trial coordinates of particle mol[i] (rows beyond atoms.size() ignored)."""
+        S = self.system.n_sites
+        x = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, S, 3)
+        n = x.shape[0]
+        m = np.ascontiguousarray(mol, dtype=np.int32)
+        t = np.zeros((n, TR_MAX_MOL_SITES, 3), dtype=np.float64)
+        tr_in = np.asarray(trial, dtype=np.float64)
+        t[:, : tr_in.shape[1], :] = tr_in
+        es = np.zeros(n, dtype=np.float64)
+        ee = np.zeros(n, dtype=np.float64)
+        self._ck(self.L.tr_delta_energy(self.h, x.ctypes.data, m.ctypes.data, t.ctypes.data, n, es.ctypes.data, ee.ctypes.data))
+        return es, ee
+
+    def rng_words(self, seeds: Sequence[int], k: int) -> np.ndarray:
+        s = np.ascontiguousarray(seeds, dtype=np.int64)
+        out = np.zeros((len(s), 3, k), dtype=np.uint32)
+        self._ck(self.L.tr_rng_words(self.h, s.ctypes.data, len(s), int(k), out.ctypes.data))
+        return out
+
+    def measure_fp64_peak(self):
+        t, mhz = C.c_double(), C.c_double()
+        self._ck(self.L.tr_measure_fp64_peak(self.h, C.byref(t), C.byref(mhz)))
+        return float(t.value), float(mhz.value)

@@ -180,7 +180,8 @@ class Config:
     particles: List[Tuple[str, int]] = field(default_factory=list)
 
     def copy(self, **kw) -> "Config":
-        return replace(self, particles=list(self.particles), **kw)
+        kw.setdefault("particles", list(self.particles))
+        return replace(self, **kw)
 
     def num_points(self) -> int:
         """Iterations of the y-loop at Main.java:191 over the whole run (finale included)."""
