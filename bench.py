@@ -222,7 +222,9 @@ def run_ours(args):
     pinned_seeds = torch.from_numpy(seeds).pin_memory()
 
     eng = Engine(local)
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: the library launches on it, so torch.cuda.Event brackets see the kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     eng.set_system(system)
     eng.set_schedules(cfg)

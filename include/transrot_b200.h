@@ -202,11 +202,13 @@ int  tr_max_points(tr_ctx *ctx, int64_t *points_per_chain, int64_t *snapshots_pe
 /* ---- parity probes: Space.calcEnergy and the eStart/eEnd loop on supplied geometries ----- */
 int  tr_total_energy(tr_ctx *ctx, const double *sites /* [n][S][3] */, int64_t n, double *energy /* [n] */);
 /* For structure i: particle mol[i] is given trial site coordinates trial[i][TR_MAX_MOL_SITES][3]
- * (first atoms.size() rows used); returns eStart and eEnd of Space.java:711-718. */
+ * (first atoms.size() rows used); returns eStart and eEnd of Space.java:711-718 and, if d_e is
+ * not NULL, eEnd - eStart exactly as the anneal kernel forms it for the Metropolis test. */
 int  tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *mol, const double *trial,
-                     int64_t n, double *e_start, double *e_end);
+                     int64_t n, double *e_start, double *e_end, double *d_e);
 /* First k 32-bit outputs of the three streams for each seed after the Main.java:34-37 fan-out:
- * out[n][3][k], drawn through the same warp-windowed generator the anneal kernel uses. */
+ * out[n][3][k], drawn through the same shared-memory ring generator the anneal kernel uses
+ * (in move-sized bursts, with one suspend/resume in the middle). */
 int  tr_rng_words(tr_ctx *ctx, const int64_t *seeds, int64_t n, int32_t k, uint32_t *out);
 
 /* ---- measurement --------------------------------------------------------------------------- */

@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/transrot_b200.h"
+#include "mt19937.cuh"
 
 namespace tr {
 
@@ -14,8 +15,13 @@ struct DevSystem {
     int n_mol, n_sites, n_types, n_moveable;
     int has_exp;                 // any pair with A != 0: keep the A*exp(-B*r) term
     int pad_;
+    int n_pos;                   // positions = 32 * W * SPL of the kernel variant in use
+    int n_lj_pos;                // positions [0, n_lj_pos) hold the sites with any non-zero C or D
+    FastMod pick_mod;            // nextInt(n_moveable) without a divide
     const int *mol_off;          // [n_mol+1]
-    const int *site_info;        // [n_sites]  mol | type << 16
+    const int *site_info;        // [n_sites]  mol | type << 16 | index-in-particle << 24
+    const int *pos_site;         // [n_pos]    site held at each (thread, slot) position, or -1
+    const unsigned char *type_lj;// [n_types]  1 = type has a non-zero C or D with some type
     const double *site_q;        // [n_sites]
     const double2 *pair_cd;      // [n_types*n_types] {C, D}
     const double2 *pair_ab;      // [n_types*n_types] {A, B}
@@ -48,8 +54,8 @@ struct ChainCtrl {
     int min_tooth;                     // Space.minEnergyToothNum
     int sched;                         // index into the schedule table
     int prop_retries;
-    int rng_pos[3];                    // streams M (Main.r), S (Space.r), R (Molecule.r)
-    int rng_gen[3];
+    MtCursor rng[3];                   // streams M (Main.r), S (Space.r), R (Molecule.r)
+    int pad_;
 };
 
 struct KParams {
@@ -58,7 +64,7 @@ struct KParams {
     ChainCtrl *ctrl;            // [n_chains]
     double *sites;              // [n_chains][S][3]
     double *com;                // [n_chains][N][3]
-    uint32_t *mt;               // [n_chains][3][624]
+    uint32_t *mt;               // [n_chains][3][2][624] ping-pong blocks
     tr_point_rec *points;       // [n_chains][max_points] or null
     double *snap_energy;        // [n_chains][max_snaps]
     int *snap_tooth;            // [n_chains][max_snaps]

@@ -6,10 +6,11 @@
 //
 // Two forms:
 //   * mt_std_*  : one thread owns a whole 624-word state (seeding, the propagate kernel).
-//   * MtStream  : one WARP owns a state that lives in global memory; lane i caches the
-//                 tempered word (base+i) of a 32-word window in a register, a draw is one
-//                 shuffle, and the 624-word block is regenerated incrementally, 32 words
-//                 at a time, in place, when a window is first touched.
+//   * MtRing    : one WARP owns a stream.  The 624-word block lives in global memory
+//                 (L2-resident) in two ping-pong buffers; the warp regenerates it 32 words at a
+//                 time (one word per lane, coalesced) and appends the TEMPERED words to a 64-word
+//                 ring in shared memory.  A draw is one broadcast LDS; the "is there enough in
+//                 the ring" test is hoisted to once per move.
 #pragma once
 #include <stdint.h>
 
@@ -18,6 +19,7 @@ namespace tr {
 constexpr int MT_N = 624;
 constexpr int MT_M = 397;
 constexpr int MT_WORDS = 625;   // exported form: 624 state words + mti
+constexpr int MT_RING = 64;     // tempered words per stream kept in shared memory
 
 __host__ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
 {
@@ -103,92 +105,136 @@ __host__ __device__ inline int64_t mt_std_next_long(uint32_t *mt, int &mti)
     return (int64_t)(hi | lo);
 }
 
-// ---- warp-windowed form --------------------------------------------------------------------
+// ---- warp form -------------------------------------------------------------------------------
+
+// What persists of one stream between launches (inside ChainCtrl).  The reference's state
+// (624 words + mti) maps to { par = 0, gen = 624, fed = mti } with the words in buffer 0.
+struct MtCursor {
+    int par;    // which of the two global buffers holds the block being consumed / generated
+    int gen;    // words of that block already generated (624 for an imported state)
+    int fed;    // words of that block already handed to the ring (= consumed, when the ring is empty)
+};
 
 #ifdef __CUDACC__
 
-// State of one stream between draws.  pos = words consumed from the current 624-block (the
-// reference's mti); gen = words of the current block already regenerated in place
-// (a state produced by the single-thread form has gen = 624).  Both are warp-uniform.
-struct MtStream {
-    uint32_t win;   // lane i: tempered word (pos & ~31) + i
-    int pos;
-    int gen;
+struct MtRing {
+    uint32_t *mt;        // global: [2][624] ping-pong buffers of this stream
+    uint32_t *ring;      // shared: [MT_RING] tempered words
+    MtCursor *cur;       // shared: persistent cursor (inside the chain's ChainCtrl copy)
+    int rd;              // next ring slot to read          (warp-uniform)
+    int avail;           // unread words in the ring        (warp-uniform)
 };
 
-// Make the window [base, base+32) current.  In-place incremental regeneration is exact:
-// word k needs old[k], old[k+1] and old[k+397] (k < 227) or new[k-227] (k >= 227), and
-// new[0] for k = 623; windows are visited in increasing order, so every "new" operand was
-// written by an earlier window and every "old" operand has not been touched yet.
-__device__ __forceinline__ void mt_fetch_window(MtStream &s, uint32_t *mt, int base, int lane)
+__device__ __forceinline__ void mt_ring_open(MtRing &g, uint32_t *mt, uint32_t *ring, MtCursor *cur)
 {
-    const int k = base + lane;
-    if (base < s.gen) {
-        s.win = (k < MT_N) ? mt_temper(mt[k]) : 0u;
-        return;
-    }
-    uint32_t cur = 0, nxt = 0, far = 0, v = 0;
-    if (k < MT_N) {
-        cur = mt[k];
-        nxt = mt[k == MT_N - 1 ? 0 : k + 1];
-        far = mt[k < MT_N - MT_M ? k + MT_M : k + MT_M - MT_N];
-    }
+    g.mt = mt; g.ring = ring; g.cur = cur; g.rd = 0; g.avail = 0;
+}
+
+// Append the next <= 32 words of the stream to the ring (all lanes of the owning warp call this).
+// Block b+1 is generated from block b held in the other buffer, so the regeneration is exact
+// and a block stays readable until the one after next is started:
+//   new[k] = (k < 227 ? old[k+397] : new[k-227]) ^ twist(old[k], k == 623 ? new[0] : old[k+1]).
+__device__ __forceinline__ void mt_ring_refill(MtRing &g, int lane)
+{
+    int par = g.cur->par, gen = g.cur->gen, fed = g.cur->fed;
     __syncwarp();
-    if (k < MT_N) {
-        uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    if (fed >= MT_N) { par ^= 1; gen = 0; fed = 0; }
+    uint32_t *B = g.mt + par * MT_N;
+    const uint32_t *O = g.mt + (par ^ 1) * MT_N;
+    const int limit = (fed < gen) ? gen : MT_N;      // load mode stops at the generated prefix
+    const int count = (limit - fed < 32) ? limit - fed : 32;
+    const int k = fed + lane;
+    uint32_t v = 0;
+    if (fed < gen) {
+        if (lane < count) v = B[k];
+    } else if (lane < count) {
+        const uint32_t a = O[k];
+        const uint32_t b = (k == MT_N - 1) ? B[0] : O[k + 1];
+        const uint32_t far = (k < MT_N - MT_M) ? O[k + MT_M] : B[k + MT_M - MT_N];
+        const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
         v = far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        mt[k] = v;
+        B[k] = v;
     }
+    if (fed >= gen) gen = fed + count;
+    if (lane < count) g.ring[(g.rd + g.avail + lane) & (MT_RING - 1)] = mt_temper(v);
+    fed += count;
+    g.avail += count;
+    if (lane == 0) { g.cur->par = par; g.cur->gen = gen; g.cur->fed = fed; }
     __syncwarp();
-    s.gen = (base + 32 < MT_N) ? base + 32 : MT_N;
-    s.win = mt_temper(v);
 }
 
-__device__ __forceinline__ void mt_stream_open(MtStream &s, uint32_t *mt, int pos, int gen, int lane)
+// Hoisted availability test: call once per move with the most words the move can draw.
+__device__ __forceinline__ void mt_ring_reserve(MtRing &g, int need, int lane)
 {
-    s.pos = pos;
-    s.gen = gen;
-    s.win = 0u;
-    if (pos < MT_N && (pos & 31) != 0) mt_fetch_window(s, mt, pos & ~31, lane);
+    while (g.avail < need) mt_ring_refill(g, lane);
 }
 
-__device__ __forceinline__ uint32_t mt_next32(MtStream &s, uint32_t *mt, int lane)
+__device__ __forceinline__ uint32_t mt_ring_next32(MtRing &g)
 {
-    if (s.pos >= MT_N) { s.pos = 0; s.gen = 0; }
-    if ((s.pos & 31) == 0) mt_fetch_window(s, mt, s.pos, lane);
-    uint32_t w = __shfl_sync(0xffffffffu, s.win, s.pos & 31);
-    s.pos++;
+    const uint32_t w = g.ring[g.rd];
+    g.rd = (g.rd + 1) & (MT_RING - 1);
+    g.avail--;
     return w;
 }
 
 // BitsStreamGenerator.nextDouble: (((long)next(26) << 26) | next(26)) * 0x1.0p-52
-__device__ __forceinline__ double mt_next_double(MtStream &s, uint32_t *mt, int lane)
+__device__ __forceinline__ double mt_ring_next_double(MtRing &g)
 {
-    uint64_t hi = (uint64_t)(mt_next32(s, mt, lane) >> 6) << 26;
-    uint64_t lo = mt_next32(s, mt, lane) >> 6;
-    return (double)(int64_t)(hi | lo) * 0x1.0p-52;
+    const uint32_t hi = mt_ring_next32(g) >> 6;
+    const uint32_t lo = mt_ring_next32(g) >> 6;
+    return (double)(int64_t)(((uint64_t)hi << 26) | lo) * 0x1.0p-52;
 }
 
-// BitsStreamGenerator.nextInt(n): power-of-two fast path, else the overflow-rejection loop
-__device__ __forceinline__ int mt_next_int(MtStream &s, uint32_t *mt, int lane, int n)
+// Exact bits % n for 0 <= bits < 2^31 by multiply-high: magic = ceil(2^(31+L) / n), L = ceil(log2 n)
+// (Granlund-Montgomery; the error term magic*n - 2^(31+L) < 2^L keeps the quotient exact below 2^31).
+struct FastMod {
+    uint32_t n, magic, shift;
+};
+
+__host__ __device__ inline FastMod fastmod_make(uint32_t n)
 {
-    if ((n & -n) == n) return (int)(((int64_t)n * (int64_t)(mt_next32(s, mt, lane) >> 1)) >> 31);
-    int bits, val;
-    do {
-        bits = (int)(mt_next32(s, mt, lane) >> 1);
-        val = bits % n;
-    } while ((int)((uint32_t)bits - (uint32_t)val + (uint32_t)(n - 1)) < 0);
-    return val;
+    FastMod f;
+    f.n = n;
+    uint32_t L = 0;
+    while ((1u << L) < n) L++;
+    f.shift = 31 + L;
+    const uint64_t p = (uint64_t)1 << f.shift;
+    f.magic = (uint32_t)((p + n - 1) / n);
+    return f;
 }
 
-// Finish the in-place regeneration of the current block so the state reads like the
-// reference's (all 624 words of the block valid, mti = pos).
-__device__ __forceinline__ void mt_stream_canonicalize(MtStream &s, uint32_t *mt, int lane)
+__host__ __device__ __forceinline__ uint32_t fastmod(const FastMod &f, uint32_t bits)
 {
-    if (s.pos >= MT_N) return;   // exhausted block: already canonical (mti = 624)
-    uint32_t keep = s.win;
-    for (int base = s.gen; base < MT_N; base += 32) mt_fetch_window(s, mt, base, lane);
-    s.win = keep;
+    const uint32_t q = (uint32_t)(((uint64_t)bits * f.magic) >> f.shift);
+    return bits - q * f.n;
+}
+
+// BitsStreamGenerator.nextInt(n): power-of-two fast path, else the overflow-rejection loop.
+// The caller reserved one word; a rejection (probability < n / 2^31) re-reserves.
+__device__ __forceinline__ int mt_ring_next_int(MtRing &g, const FastMod &f, int lane)
+{
+    const int n = (int)f.n;
+    if ((n & -n) == n) return (int)(((int64_t)n * (int64_t)(mt_ring_next32(g) >> 1)) >> 31);
+    for (;;) {
+        const int bits = (int)(mt_ring_next32(g) >> 1);
+        const int val = (int)fastmod(f, (uint32_t)bits);
+        if ((int)((uint32_t)bits - (uint32_t)val + (uint32_t)(n - 1)) >= 0) return val;
+        mt_ring_reserve(g, 1, lane);
+    }
+}
+
+// Give the unread ring words back to the cursor so nothing but (par, gen, fed) has to persist.
+__device__ __forceinline__ void mt_ring_close(MtRing &g, int lane)
+{
+    __syncwarp();
+    if (lane == 0) {
+        MtCursor c = *g.cur;
+        if (g.avail <= c.fed) c.fed -= g.avail;
+        else { c.par ^= 1; c.fed = MT_N - (g.avail - c.fed); c.gen = MT_N; }   // back into the previous block
+        *g.cur = c;
+    }
+    g.avail = 0;
+    __syncwarp();
 }
 
 #endif  // __CUDACC__

@@ -56,9 +56,10 @@ __global__ void init_chains_kernel(InitParams ip)
     const long long chain = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (chain >= ip.n_chains) return;
     const DevSystem &sys = ip.sys;
-    uint32_t *mtM = ip.mt + ((size_t)chain * 3 + STREAM_M) * MT_N;
-    uint32_t *mtS = ip.mt + ((size_t)chain * 3 + STREAM_S) * MT_N;
-    uint32_t *mtR = ip.mt + ((size_t)chain * 3 + STREAM_R) * MT_N;
+    // buffer 0 of each stream's ping-pong pair receives the reference-form state
+    uint32_t *mtM = ip.mt + ((size_t)chain * 3 + STREAM_M) * 2 * MT_N;
+    uint32_t *mtS = ip.mt + ((size_t)chain * 3 + STREAM_S) * 2 * MT_N;
+    uint32_t *mtR = ip.mt + ((size_t)chain * 3 + STREAM_R) * 2 * MT_N;
     int posM = MT_N, posS = MT_N, posR = MT_N;
     if (ip.seeds) {
         mt_std_seed_long(mtM, ip.seeds[chain]);          // seedGenerator, Main.java:24,34
@@ -163,8 +164,9 @@ __global__ void init_chains_kernel(InitParams ip)
     c.ptsPerTooth = sch.static_temp ? 1 : sch.points_per_tooth;   // Main.java:74-76
     c.sched = si;
     c.prop_retries = retries;
-    c.rng_pos[STREAM_M] = posM; c.rng_pos[STREAM_S] = posS; c.rng_pos[STREAM_R] = posR;
-    c.rng_gen[STREAM_M] = MT_N; c.rng_gen[STREAM_S] = MT_N; c.rng_gen[STREAM_R] = MT_N;
+    c.rng[STREAM_M].par = 0; c.rng[STREAM_M].gen = MT_N; c.rng[STREAM_M].fed = posM;
+    c.rng[STREAM_S].par = 0; c.rng[STREAM_S].gen = MT_N; c.rng[STREAM_S].fed = posS;
+    c.rng[STREAM_R].par = 0; c.rng[STREAM_R].gen = MT_N; c.rng[STREAM_R].fed = posR;
     ip.ctrl[chain] = c;
 }
 
@@ -176,7 +178,7 @@ template <int SPL, int W, bool HAS_EXP>
 __global__ void __launch_bounds__(32 * W) total_energy_kernel(DevSystem sys, const double *sites, long long n, double *out, int smem_tables)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemTables tb = carve_tables(smem, sys, HAS_EXP);
+    const SmemTables tb = carve_tables(smem, sys);
     load_tables(tb, sys, HAS_EXP);
     const SmemChain sc = carve_chain(smem + smem_tables, sys, W);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -184,92 +186,129 @@ __global__ void __launch_bounds__(32 * W) total_energy_kernel(DevSystem sys, con
     for (long long i = blockIdx.x; i < n; i += gridDim.x) {
         SiteRegs<SPL> R;
         sites_from_global<SPL, W>(R, sites + (size_t)i * sys.n_sites * 3, sys, tid);
-        sites_to_scratch<SPL, W>(R, sc.scratch, tid, sys.n_sites);
+        sites_to_scratch<SPL, W>(R, sc.scratch, sys.pos_site, tid);
         const double e = team_total_energy<SPL, W, HAS_EXP>(R, sc.scratch, sys, tb.cd, tb.ab, sc.part, warp, lane);
         if (tid == 0) out[i] = e;
         __syncthreads();
     }
 }
 
-// eStart / eEnd (Space.java:711-718) for supplied trial coordinates of one particle.
+// eStart / eEnd (Space.java:711-718) for supplied trial coordinates of one particle: the
+// staging + move_energy + reduction path of the anneal kernel.
 template <int SPL, int W, bool HAS_EXP>
 __global__ void __launch_bounds__(32 * W) delta_energy_kernel(DevSystem sys, const double *sites, const int *mol, const double *trial,
-                                                              long long n, double *e_start, double *e_end, int smem_tables)
+                                                              long long n, double *e_start, double *e_end, double *d_e, int smem_tables)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemTables tb = carve_tables(smem, sys, HAS_EXP);
+    const SmemTables tb = carve_tables(smem, sys);
     load_tables(tb, sys, HAS_EXP);
     const SmemChain sc = carve_chain(smem + smem_tables, sys, W);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int TPC = 32 * W;
+    const int lj_slots = (sys.n_lj_pos + TPC - 1) / TPC;
     __syncthreads();
     for (long long i = blockIdx.x; i < n; i += gridDim.x) {
         SiteRegs<SPL> R;
         sites_from_global<SPL, W>(R, sites + (size_t)i * sys.n_sites * 3, sys, tid);
         const int m = mol[i];
-        const int off = tb.mol_off[m], sm = tb.mol_off[m + 1] - off;
+        const int sm = tb.mol_off[m + 1] - tb.mol_off[m];
         const double *tr_i = trial + (size_t)i * TR_MAX_MOL_SITES * 3;
 #pragma unroll
         for (int k = 0; k < SPL; k++) {
-            const int a = tid + k * TPC - off;
-            if (a >= 0 && a < sm) {
+            if (info_mol(R.info[k]) == m) {
+                const int a = info_atom(R.info[k]);
                 StageSite st;
                 st.ox = R.x[k]; st.oy = R.y[k]; st.oz = R.z[k];
                 st.nx = tr_i[3 * a]; st.ny = tr_i[3 * a + 1]; st.nz = tr_i[3 * a + 2];
                 st.kq = __dmul_rn(K_VALUE, R.q[k]);
-                st.type = R.info[k] >> 16; st.pad = 0;
+                st.type = info_type(R.info[k]); st.lj = info_lj(R.info[k]);
                 sc.stage[a] = st;
             }
         }
         __syncthreads();
         double eS, eE;
-        move_energy<SPL, HAS_EXP>(R, sc.stage, sm, m, tb.cd, tb.ab, sys.n_types, eS, eE);
-        team_sum2<W>(eS, eE, sc.part, warp, lane);
-        if (tid == 0) { e_start[i] = eS; e_end[i] = eE; }
+        move_energy<SPL, HAS_EXP>(R, sc.stage, sm, m, tb.cd, tb.ab, sys.n_types, lj_slots, eS, eE);
+        const double dE = team_sum<W>(eE - eS, sc.part, warp, lane);
+        __syncthreads();
+        eS = team_sum<W>(eS, sc.part, warp, lane);
+        __syncthreads();
+        eE = team_sum<W>(eE, sc.part, warp, lane);
+        if (tid == 0) { e_start[i] = eS; e_end[i] = eE; d_e[i] = dE; }
         __syncthreads();
     }
 }
 
-// First k outputs of the three streams of each seed, drawn through the warp-windowed
-// generator (one warp per seed; `mt` is scratch [n][3][624]).
-__global__ void rng_words_kernel(const long long *seeds, long long n, int k, uint32_t *mt, uint32_t *out)
+// First k outputs of the three streams of each seed, drawn through the ring generator the anneal
+// kernel uses (one warp per seed; `mt` is scratch [n][3][2][624]), in bursts of the sizes a move uses.
+__global__ void __launch_bounds__(128) rng_words_kernel(const long long *seeds, long long n, int k, uint32_t *mt, uint32_t *out)
 {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ uint32_t s_ring[4][MT_RING];
+    __shared__ MtCursor s_cur[4];
+    const int w = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 4 + w;
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
-    uint32_t *st = mt + (size_t)i * 3 * MT_N;
+    uint32_t *st = mt + (size_t)i * 3 * 2 * MT_N;
     if (lane == 0) {
         mt_std_seed_long(st, seeds[i]);
         int mti = MT_N;
         const int64_t s0 = mt_std_next_long(st, mti), s1 = mt_std_next_long(st, mti), s2 = mt_std_next_long(st, mti);
         mt_std_seed_long(st, s0);
-        mt_std_seed_long(st + MT_N, s1);
-        mt_std_seed_long(st + 2 * MT_N, s2);
+        mt_std_seed_long(st + 2 * MT_N, s1);
+        mt_std_seed_long(st + 4 * MT_N, s2);
     }
     __syncwarp();
     for (int s = 0; s < 3; s++) {
-        MtStream g;
-        mt_stream_open(g, st + s * MT_N, MT_N, MT_N, lane);
-        for (int j = 0; j < k; j++) {
-            const uint32_t w = mt_next32(g, st + s * MT_N, lane);
-            if (lane == 0) out[((size_t)i * 3 + s) * k + j] = w;
+        if (lane == 0) { s_cur[w].par = 0; s_cur[w].gen = MT_N; s_cur[w].fed = MT_N; }
+        __syncwarp();
+        MtRing g;
+        mt_ring_open(g, st + s * 2 * MT_N, s_ring[w], &s_cur[w]);
+        int j = 0, burst = 1;
+        bool resumed = false;
+        while (j < k) {
+            const int need = (k - j < burst) ? k - j : burst;
+            mt_ring_reserve(g, need, lane);
+            for (int b = 0; b < need; b++, j++) {
+                const uint32_t v = mt_ring_next32(g);
+                if (lane == 0) out[((size_t)i * 3 + s) * k + j] = v;
+            }
+            burst = burst % 11 + 1;      // 1..11 words per reservation, like the moves
+            if (!resumed && j >= k / 2) {     // suspend / resume, as between two launches
+                mt_ring_close(g, lane);
+                mt_ring_open(g, st + s * 2 * MT_N, s_ring[w], &s_cur[w]);
+                resumed = true;
+            }
         }
+        __syncwarp();
     }
 }
 
-// Finish the in-place regeneration of every stream so the exported state equals the
-// reference's (624 valid words + mti); keeps the chains resumable.
-__global__ void rng_canonicalize_kernel(ChainCtrl *ctrl, uint32_t *mt, long long n_chains)
+// The reference's view of every stream (624 words of the current block + mti).  Completes the
+// block in place first (harmless: the cursor records it), so chains stay resumable.
+__global__ void __launch_bounds__(128) rng_export_kernel(ChainCtrl *ctrl, uint32_t *mt, long long n_chains, uint32_t *out)
 {
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= n_chains) return;
     for (int s = 0; s < 3; s++) {
-        MtStream g;
-        g.win = 0; g.pos = ctrl[i].rng_pos[s]; g.gen = ctrl[i].rng_gen[s];
-        mt_stream_canonicalize(g, mt + ((size_t)i * 3 + s) * MT_N, lane);
+        MtCursor c = ctrl[i].rng[s];
+        uint32_t *B = mt + (((size_t)i * 3 + s) * 2 + c.par) * MT_N;
+        const uint32_t *O = mt + (((size_t)i * 3 + s) * 2 + (c.par ^ 1)) * MT_N;
+        for (int base = c.gen; base < MT_N; base += 32) {       // gen is window-aligned whenever it is < 624
+            const int k = base + lane;
+            if (k < MT_N) {
+                const uint32_t a = O[k];
+                const uint32_t b = (k == MT_N - 1) ? B[0] : O[k + 1];
+                const uint32_t far = (k < MT_N - MT_M) ? O[k + MT_M] : B[k + MT_M - MT_N];
+                const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+                B[k] = far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            __syncwarp();
+        }
+        uint32_t *dst = out + ((size_t)i * 3 + s) * MT_WORDS;
+        for (int k = lane; k < MT_N; k += 32) dst[k] = B[k];
+        if (lane == 0) { dst[MT_N] = (uint32_t)c.fed; ctrl[i].rng[s].gen = MT_N; }
         __syncwarp();
-        if (lane == 0 && g.pos < MT_N) ctrl[i].rng_gen[s] = MT_N;
     }
 }
 

@@ -58,8 +58,10 @@ struct tr_ctx {
     DevBuf<int> d_mol_off, d_site_info, d_moveable, d_site_ghost;
     DevBuf<double> d_site_q, d_mol_radius, d_site_def, d_site_mass;
     DevBuf<double2> d_pair_cd, d_pair_ab;
+    DevBuf<int> d_pos_site;
     bool have_propagate_data = false;
-    std::vector<int> h_mol_off;
+    std::vector<int> h_mol_off, h_site_lj;
+    Variant prepared{0, 0};
 
     // schedules
     DevBuf<tr_schedule> d_sched;
@@ -133,18 +135,58 @@ bool pick_variant(const tr_ctx *ctx, int n_sites, int tpc, Variant *out)
 
 int chains_per_block(const Variant &v) { return v.W == 1 ? 4 : 1; }
 
+// Site -> (thread, slot) permutation of a kernel variant: sites with Lennard-Jones parameters first, so that
+// the trailing slots are Coulomb-only for every thread (anneal.cuh).
+int prepare_variant(tr_ctx *ctx, const Variant &v)
+{
+    if (ctx->prepared.W == v.W && ctx->prepared.SPL == v.SPL) return TR_OK;
+    const int n_pos = 32 * v.W * v.SPL, S = ctx->sys.n_sites;
+    std::vector<int> pos(n_pos, -1);
+    int p = 0, n_lj = 0;
+    for (int i = 0; i < S; i++) if (ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
+    n_lj = p;
+    for (int i = 0; i < S; i++) if (!ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (int r = upload(ctx, ctx->d_pos_site, pos.data(), pos.size())) return r;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->sys.pos_site = ctx->d_pos_site.p;
+    ctx->sys.n_pos = n_pos;
+    ctx->sys.n_lj_pos = n_lj;
+    ctx->prepared = v;
+    return TR_OK;
+}
+
 // ---- kernel dispatch -----------------------------------------------------------------------
+
+template <int W, int SPL> struct MinBlocks { static constexpr int value = 1; };
+// blocks per SM the register budget is squeezed for: 7 x 128 threads = 28 chains per SM lets
+// 4096 warp-per-chain chains be resident in one wave on 148 SMs
+template <> struct MinBlocks<1, 1> { static constexpr int value = 7; };
+template <> struct MinBlocks<1, 2> { static constexpr int value = 7; };
+template <> struct MinBlocks<1, 4> { static constexpr int value = 5; };
+template <> struct MinBlocks<1, 6> { static constexpr int value = 4; };
+template <> struct MinBlocks<4, 2> { static constexpr int value = 6; };
+template <> struct MinBlocks<4, 6> { static constexpr int value = 3; };
+template <> struct MinBlocks<8, 3> { static constexpr int value = 2; };
+template <> struct MinBlocks<8, 6> { static constexpr int value = 1; };
 
 template <int SPL, int W, bool HAS_EXP>
 cudaError_t launch_anneal_t(tr_ctx *ctx, const KParams &P)
 {
-    constexpr int CPB = (W == 1) ? 4 : 1;
-    auto kern = anneal_kernel<SPL, W, HAS_EXP, CPB>;
+    constexpr int CPB = LaunchCfg<W>::CPB;
+    constexpr int MINB = MinBlocks<W, SPL>::value;
     const int smem = P.smem_tables + CPB * P.smem_per_chain;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((P.n_chains + CPB - 1) / CPB);
-    kern<<<blocks, 32 * W * CPB, smem, ctx->stream>>>(P);
+    cudaError_t e;
+    if (P.trace) {
+        auto kern = anneal_kernel<SPL, W, HAS_EXP, true, 1>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+        kern<<<blocks, 32 * W * CPB, smem, ctx->stream>>>(P);
+    } else {
+        auto kern = anneal_kernel<SPL, W, HAS_EXP, false, MINB>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+        kern<<<blocks, 32 * W * CPB, smem, ctx->stream>>>(P);
+    }
     return cudaGetLastError();
 }
 
@@ -162,14 +204,14 @@ cudaError_t launch_total_t(tr_ctx *ctx, const double *d_sites, long long n, doub
 
 template <int SPL, int W, bool HAS_EXP>
 cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol, const double *d_trial, long long n,
-                           double *d_es, double *d_ee, int smem_tables, int smem_chain)
+                           double *d_es, double *d_ee, double *d_de, int smem_tables, int smem_chain)
 {
     auto kern = delta_energy_kernel<SPL, W, HAS_EXP>;
     const int smem = smem_tables + smem_chain;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
-    kern<<<blocks, 32 * W, smem, ctx->stream>>>(ctx->sys, d_sites, d_mol, d_trial, n, d_es, d_ee, smem_tables);
+    kern<<<blocks, 32 * W, smem, ctx->stream>>>(ctx->sys, d_sites, d_mol, d_trial, n, d_es, d_ee, d_de, smem_tables);
     return cudaGetLastError();
 }
 
@@ -219,6 +261,7 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
         return fail(ctx, TR_ELIMIT, "Error: %d sites do not fit %d threads per chain (limit %d sites)", ctx->sys.n_sites,
                     ctx->threads_per_chain, TR_MAX_SITES);
     ctx->variant = v;
+    if (int r = prepare_variant(ctx, v)) return r;
     const int smem = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp) +
                      chains_per_block(v) * smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
     if (smem > ctx->max_smem_optin)
@@ -240,7 +283,7 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
     CK(ctx, ctx->d_ctrl.alloc(C));
     CK(ctx, ctx->d_sites.alloc(C * S * 3));
     CK(ctx, ctx->d_com.alloc(C * N * 3));
-    CK(ctx, ctx->d_mt.alloc(C * 3 * MT_N));
+    CK(ctx, ctx->d_mt.alloc(C * 3 * 2 * MT_N));
     CK(ctx, ctx->d_snap_energy.alloc(C * max_snaps));
     CK(ctx, ctx->d_snap_tooth.alloc(C * max_snaps));
     CK(ctx, cudaMemsetAsync(ctx->d_snap_tooth.p, 0xff, C * max_snaps * sizeof(int), ctx->stream));
@@ -373,7 +416,7 @@ extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
         for (int i = a; i < b; i++) {
             NEED(ctx, s->site_type[i] >= 0 && s->site_type[i] < s->n_types, "Error: site %d has type %d outside 0..%d", i,
                  s->site_type[i], s->n_types - 1);
-            info[(size_t)i] = m | (s->site_type[i] << 16);
+            info[(size_t)i] = m | (s->site_type[i] << 16) | ((i - a) << 24);
         }
     }
     for (int k = 0; k < s->n_moveable; k++)
@@ -386,9 +429,23 @@ extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
         cd[i] = make_double2(s->pair_abcd[4 * i + 2], s->pair_abcd[4 * i + 3]);
         if (s->pair_abcd[4 * i] != 0.0) has_exp = 1;   // NaN (an undefined pair) also keeps the full formula
     }
+    // a type "has Lennard-Jones" when C or D is non-zero (or NaN) against any type; with a Born-Mayer term
+    // anywhere every site takes the full formula
+    std::vector<int> type_lj((size_t)s->n_types, 0);
+    for (int t1 = 0; t1 < s->n_types; t1++)
+        for (int t2 = 0; t2 < s->n_types; t2++) {
+            const double2 v = cd[(size_t)t1 * s->n_types + t2];
+            if (!(v.x == 0.0) || !(v.y == 0.0) || has_exp) type_lj[(size_t)t1] = 1;
+        }
+    ctx->h_site_lj.assign((size_t)s->n_sites, 0);
+    for (int i = 0; i < s->n_sites; i++) {
+        ctx->h_site_lj[(size_t)i] = type_lj[(size_t)s->site_type[i]];
+        info[(size_t)i] |= type_lj[(size_t)s->site_type[i]] << 29;
+    }
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_system = false;
     ctx->n_chains = 0;
+    ctx->prepared = Variant{0, 0};
     ctx->h_mol_off.assign(s->mol_site_off, s->mol_site_off + s->n_mol + 1);
     if (int r = upload(ctx, ctx->d_mol_off, s->mol_site_off, (size_t)s->n_mol + 1)) return r;
     if (int r = upload(ctx, ctx->d_site_info, info.data(), info.size())) return r;
@@ -407,6 +464,8 @@ extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
     DevSystem &d = ctx->sys;
     d.n_mol = s->n_mol; d.n_sites = s->n_sites; d.n_types = s->n_types; d.n_moveable = s->n_moveable;
     d.has_exp = has_exp; d.pad_ = 0;
+    d.n_pos = 0; d.n_lj_pos = 0; d.pos_site = nullptr; d.type_lj = nullptr;
+    d.pick_mod = fastmod_make((uint32_t)s->n_moveable);
     d.mol_off = ctx->d_mol_off.p; d.site_info = ctx->d_site_info.p; d.site_q = ctx->d_site_q.p;
     d.pair_cd = ctx->d_pair_cd.p; d.pair_ab = ctx->d_pair_ab.p; d.moveable = ctx->d_moveable.p;
     d.mol_radius = ctx->d_mol_radius.p; d.site_def = ctx->d_site_def.p; d.site_mass = ctx->d_site_mass.p;
@@ -500,10 +559,10 @@ extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t fi
     std::vector<uint32_t> words;
     std::vector<int> pos;
     if (mt_state) {
-        words.resize((size_t)n_chains * 3 * MT_N);
+        words.assign((size_t)n_chains * 3 * 2 * MT_N, 0u);
         pos.resize((size_t)n_chains * 3);
         for (size_t i = 0; i < (size_t)n_chains * 3; i++) {
-            memcpy(words.data() + i * MT_N, mt_state + i * MT_WORDS, MT_N * 4);
+            memcpy(words.data() + i * 2 * MT_N, mt_state + i * MT_WORDS, MT_N * 4);   // buffer 0 of the ping-pong pair
             const uint32_t mti = mt_state[i * MT_WORDS + MT_N];
             NEED(ctx, mti <= (uint32_t)MT_N, "Error: RNG state %zu has mti %u > 624", i, mti);
             pos[i] = (int)mti;
@@ -674,17 +733,14 @@ extern "C" int tr_get_rng_state(tr_ctx *ctx, uint32_t *out)
     if (int r = bind(ctx)) return r;
     if (int r = need_chains(ctx)) return r;
     NEED(ctx, out != nullptr, "Error: tr_get_rng_state: out is NULL");
+    DevBuf<uint32_t> d_out;
+    CK(ctx, d_out.alloc((size_t)ctx->n_chains * 3 * MT_WORDS));
     const long long threads = ctx->n_chains * 32;
-    rng_canonicalize_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ctrl.p, ctx->d_mt.p, ctx->n_chains);
+    rng_export_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ctrl.p, ctx->d_mt.p, ctx->n_chains, d_out.p);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
-    std::vector<ChainCtrl> ctrl((size_t)ctx->n_chains);
-    CK(ctx, cudaMemcpyAsync(ctrl.data(), ctx->d_ctrl.p, ctrl.size() * sizeof(ChainCtrl), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaMemcpy2DAsync(out, MT_WORDS * 4, ctx->d_mt.p, MT_N * 4, MT_N * 4, (size_t)ctx->n_chains * 3, cudaMemcpyDeviceToHost,
-                              ctx->stream));
+    CK(ctx, cudaMemcpyAsync(out, d_out.p, (size_t)ctx->n_chains * 3 * MT_WORDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    for (size_t c = 0; c < ctrl.size(); c++)
-        for (int s = 0; s < 3; s++) out[(c * 3 + s) * MT_WORDS + MT_N] = (uint32_t)ctrl[c].rng_pos[s];
     return TR_OK;
 }
 
@@ -744,6 +800,9 @@ extern "C" int tr_total_energy(tr_ctx *ctx, const double *sites, int64_t n, doub
     NEED(ctx, sites && energy && n > 0, "Error: tr_total_energy: bad arguments");
     Variant v;
     if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v)) return fail(ctx, TR_ELIMIT, "Error: system too large");
+    NEED(ctx, ctx->n_chains == 0 || (v.W == ctx->variant.W && v.SPL == ctx->variant.SPL),
+         "Error: threads_per_chain changed while chains are live; re-initialise the chains first");
+    if (int r = prepare_variant(ctx, v)) return r;
     DevBuf<double> d_sites, d_out;
     const size_t S3 = (size_t)ctx->sys.n_sites * 3;
     CK(ctx, d_sites.alloc((size_t)n * S3));
@@ -763,7 +822,7 @@ extern "C" int tr_total_energy(tr_ctx *ctx, const double *sites, int64_t n, doub
 }
 
 extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *mol, const double *trial, int64_t n, double *e_start,
-                               double *e_end)
+                               double *e_end, double *d_e)
 {
     if (!ctx) return TR_EINVAL;
     if (int r = bind(ctx)) return r;
@@ -772,7 +831,10 @@ extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *
     for (int64_t i = 0; i < n; i++) NEED(ctx, mol[i] >= 0 && mol[i] < ctx->sys.n_mol, "Error: mol[%lld] out of range", (long long)i);
     Variant v;
     if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v)) return fail(ctx, TR_ELIMIT, "Error: system too large");
-    DevBuf<double> d_sites, d_trial, d_es, d_ee;
+    NEED(ctx, ctx->n_chains == 0 || (v.W == ctx->variant.W && v.SPL == ctx->variant.SPL),
+         "Error: threads_per_chain changed while chains are live; re-initialise the chains first");
+    if (int r = prepare_variant(ctx, v)) return r;
+    DevBuf<double> d_sites, d_trial, d_es, d_ee, d_de;
     DevBuf<int> d_mol;
     const size_t S3 = (size_t)ctx->sys.n_sites * 3, T3 = (size_t)TR_MAX_MOL_SITES * 3;
     CK(ctx, d_sites.alloc((size_t)n * S3));
@@ -780,19 +842,21 @@ extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *
     CK(ctx, d_mol.alloc((size_t)n));
     CK(ctx, d_es.alloc((size_t)n));
     CK(ctx, d_ee.alloc((size_t)n));
+    CK(ctx, d_de.alloc((size_t)n));
     CK(ctx, cudaMemcpyAsync(d_sites.p, sites, (size_t)n * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d_trial.p, trial, (size_t)n * T3 * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d_mol.p, mol, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     const int st = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp);
     const int sc = smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
     cudaError_t e;
-#define CALL_DELTA(SPL, W, HE) launch_delta_t<SPL, W, HE>(ctx, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, st, sc)
+#define CALL_DELTA(SPL, W, HE) launch_delta_t<SPL, W, HE>(ctx, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, d_de.p, st, sc)
     TR_DISPATCH(v, ctx->sys.has_exp, CALL_DELTA);
 #undef CALL_DELTA
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: delta-energy kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
     CK(ctx, cudaMemcpyAsync(e_start, d_es.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaMemcpyAsync(e_end, d_ee.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_e) CK(ctx, cudaMemcpyAsync(d_e, d_de.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return TR_OK;
 }
@@ -805,11 +869,10 @@ extern "C" int tr_rng_words(tr_ctx *ctx, const int64_t *seeds, int64_t n, int32_
     DevBuf<long long> d_seeds;
     DevBuf<uint32_t> d_mt, d_out;
     CK(ctx, d_seeds.alloc((size_t)n));
-    CK(ctx, d_mt.alloc((size_t)n * 3 * MT_N));
+    CK(ctx, d_mt.alloc((size_t)n * 3 * 2 * MT_N));
     CK(ctx, d_out.alloc((size_t)n * 3 * (size_t)k));
     CK(ctx, cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const long long threads = n * 32;
-    rng_words_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(d_seeds.p, n, k, d_mt.p, d_out.p);
+    rng_words_kernel<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(d_seeds.p, n, k, d_mt.p, d_out.p);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpyAsync(out, d_out.p, (size_t)n * 3 * (size_t)k * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -87,7 +87,7 @@ _SIGNATURES = {
     "tr_get_min_structure": [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)],
     "tr_max_points": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "tr_total_energy": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
-    "tr_delta_energy": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
+    "tr_delta_energy": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "tr_rng_words": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p],
     "tr_measure_fp64_peak": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
 }
@@ -320,8 +320,9 @@ class Engine:
         t[:, : tr_in.shape[1], :] = tr_in
         es = np.zeros(n, dtype=np.float64)
         ee = np.zeros(n, dtype=np.float64)
-        self._ck(self.L.tr_delta_energy(self.h, x.ctypes.data, m.ctypes.data, t.ctypes.data, n, es.ctypes.data, ee.ctypes.data))
-        return es, ee
+        de = np.zeros(n, dtype=np.float64)
+        self._ck(self.L.tr_delta_energy(self.h, x.ctypes.data, m.ctypes.data, t.ctypes.data, n, es.ctypes.data, ee.ctypes.data, de.ctypes.data))
+        return es, ee, de
 
     def rng_words(self, seeds: Sequence[int], k: int) -> np.ndarray:
         s = np.ascontiguousarray(seeds, dtype=np.int64)
