@@ -156,7 +156,8 @@ int  tr_set_system(tr_ctx *ctx, const tr_system *sys);
 int  tr_set_schedules(tr_ctx *ctx, const tr_schedule *sched, int32_t n_sched);
 /* Options, set before tr_init_*:  trace_moves = decision-trace records kept per chain;
  * record_points / record_snapshots = keep per-point records / write(n) structures;
- * threads_per_chain = 0 (auto), 32 (warp per chain) or 64/128/256 (block per chain). */
+ * threads_per_chain = 0 (auto), 16 (half-warp per chain, <= 64 sites), 32 (warp per chain,
+ * <= 192 sites) or 128/256 (block per chain). */
 int  tr_set_options(tr_ctx *ctx, int64_t trace_moves, int32_t record_points,
                     int32_t record_snapshots, int32_t threads_per_chain);
 

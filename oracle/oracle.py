@@ -146,6 +146,7 @@ def lib() -> C.CDLL:
         "or_get_coords": (None, [vp, dp, dp]),
         "or_set_coords": (None, [vp, dp, dp]),
         "or_calc_energy": (C.c_double, [vp]),
+        "or_calc_energy_abs": (C.c_double, [vp, dp]),
         "or_mol_energy": (C.c_double, [vp, C.c_int, C.c_int]),
         "or_move": (C.c_int, [vp, C.c_int, C.c_double, C.c_double, dp, vp]),
         "or_rotate": (C.c_int, [vp, C.c_int, C.c_double, C.c_double, dp, vp]),
@@ -355,6 +356,12 @@ class OracleSpace:
     # ---- energies and moves
     def calc_energy(self) -> float:
         return float(self.L.or_calc_energy(self.h))
+
+    def calc_energy_abs(self):
+        """(calcEnergy(), sum of |pair term|): the second value is the conditioning scale of the first."""
+        a = C.c_double()
+        e = float(self.L.or_calc_energy_abs(self.h, C.byref(a)))
+        return e, float(a.value)
 
     def mol_energy(self, m: int, n: int) -> float:
         return float(self.L.or_mol_energy(self.h, m, n))

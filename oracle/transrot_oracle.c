@@ -384,6 +384,15 @@ double or_calc_energy(const or_space *cs)   /* Space.java:648-658 */
     return totEnergy;
 }
 
+double or_calc_energy_abs(const or_space *cs, double *abs_sum)   /* test aid: calcEnergy + sum of |pair term| */
+{
+    or_space *s = (or_space *)cs;
+    s->abs_acc = 0.0;
+    double e = or_calc_energy(cs);
+    if (abs_sum) *abs_sum = s->abs_acc;
+    return e;
+}
+
 double or_mol_energy(const or_space *cs, int m, int n)
 {
     or_space *s = (or_space *)cs;

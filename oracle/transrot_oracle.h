@@ -136,6 +136,8 @@ void or_set_coords(or_space *s, const double *sites, const double *com);
 
 /* Space.calcEnergy (Space.java:648-658). */
 double or_calc_energy(const or_space *s);
+/* Test aid: calcEnergy plus the sum of |pair term|, the conditioning scale of that sum. */
+double or_calc_energy_abs(const or_space *s, double *abs_sum);
 /* Molecule.calcEnergy(m -> n) (Molecule.java:99-107). */
 double or_mol_energy(const or_space *s, int m, int n);
 /* Space.move / Space.rotate (Space.java:660-734); rec may be NULL. */

@@ -3,18 +3,22 @@
 // the Atom pair potential (Atom.java:91-119) and Space.calcEnergy (Space.java:648-658).
 //
 // Mapping.  A chain (one independent annealing run = one reference JVM process) is owned by
-// a TEAM of W warps (W = 1: warp per chain, several chains per block; W > 1: block per
-// chain).  The sites of `space` live in REGISTERS for the whole launch: position p of a
-// host-chosen permutation sits in team thread (p mod 32W), slot (p div 32W).  The permutation
-// puts the sites that have Lennard-Jones parameters first, so whole slots are Coulomb-only
-// and skip the r^-6 / r^-12 arithmetic (warp-uniform decision per staged site x slot).
-// Per move the moved particle's old and trial site coordinates are staged in shared memory
-// (<= TR_MAX_MOL_SITES entries, read back as broadcasts), every thread evaluates the site
-// pairs between its own sites and the staged ones in FP64, and eEnd - eStart is reduced with
-// shuffles (plus one shared-memory hop when W > 1).  The three MT19937 streams stay in global
-// memory (L2-resident) behind 64-word rings of tempered words in shared memory (mt19937.cuh).
-// The schedule cursor lives in shared memory, so a launch can stop after any move and the
-// next one resumes bit-identically.
+// a TEAM: L = 16 or 32 lanes of one warp (several chains per block; L = 16 puts two chains in
+// a warp, which shares the per-move scalar work and leaves 146 registers per thread at the
+// occupancy that keeps 4096 chains resident in one wave), or W > 1 whole warps (block per
+// chain, for clusters of hundreds of sites).
+// Data.  A chain's site coordinates live in SHARED MEMORY as {x, y, z, q} records in a
+// host-chosen position order: position p belongs to team thread (p mod TPC), slot (p div TPC),
+// and the sites that have Lennard-Jones parameters come first, so whole slots are Coulomb-only
+// and skip the r^-6 / r^-12 arithmetic.  Per move, lanes 0..s_m-1 build the trial geometry of the
+// moved particle's sites and stage old + trial coordinates (<= TR_MAX_MOL_SITES entries, read
+// back as broadcasts); every thread then evaluates the site pairs between its own positions and
+// the staged sites in FP64 (pairs inside the moved particle are neutralised by a zero charge and
+// a unit offset on r^2 rather than by branches), and eEnd - eStart is reduced with shuffles
+// (plus one shared-memory hop when W > 1).  The three MT19937 streams stay in global memory
+// (L2-resident) behind 64-word rings of tempered words in shared memory (mt19937.cuh).  The
+// schedule cursor lives in shared memory, so a launch can stop after any move and the next one
+// resumes bit-identically.
 #pragma once
 #include <math.h>
 #include "device_types.cuh"
@@ -22,11 +26,19 @@
 
 namespace tr {
 
+template <int L, int W>
+struct Team {
+    static_assert(W == 1 || L == 32, "multi-warp teams use whole warps");
+    static constexpr int TPC = (W > 1) ? 32 * W : L;     // threads per chain
+    static constexpr int CPB = (W > 1) ? 1 : 4;          // chains per block
+    static constexpr int BLOCK = TPC * CPB;
+};
+
 struct __align__(16) StageSite {
     double ox, oy, oz;   // committed coordinates (after the rotateTemp round trip)
     double nx, ny, nz;   // trial coordinates (Atom.tempx/y/z)
     double kq;           // Atom.kTimesQ = K_VALUE * q
-    int type;
+    int row;             // byte offset of this site type's row in the pair tables
     int lj;              // type has Lennard-Jones parameters with some type
 };
 
@@ -38,18 +50,32 @@ struct MoveDesc {        // W > 1 only: what warp 0 decided, broadcast through s
     int magwalk;
 };
 
-template <int SPL>
-struct SiteRegs {
-    double x[SPL], y[SPL], z[SPL], q[SPL];
-    int info[SPL];       // mol | type << 16 | index-in-particle << 24 | has-LJ << 29, or INFO_UNUSED
+// Fixed-size part of a chain's shared-memory region: every field sits at a compile-time offset
+// from one base register.  com[N*3] and sites[n_pos] follow it.
+struct __align__(16) ChainSmem {
+    StageSite stage[TR_MAX_MOL_SITES];
+    ChainCtrl ctrl;
+    uint32_t ring[3][MT_RING];
+    double part[8];
+    MoveDesc desc;
+    int flag[2];
+    unsigned long long thr_rot, thr_trans;   // u >= magwalkProb as 52-bit integer compares
+    double bound_hi, pad_;                   // 0.75 * spaceLen (Space.java:663,706)
 };
 
-constexpr int INFO_UNUSED = 0xffff;   // mol field of a slot that holds no site (type 0, so table lookups stay in range)
+struct __align__(16) SiteRec { double x, y, z, q; };   // one position of a chain
+
+// Per-position info word: mol | type << 16 | index-in-particle << 24 | has-LJ << 29.  An empty position has
+// mol = INFO_UNUSED, type = n_types (the all-zero table column), q = 0 and far-away coordinates, so it adds
+// exactly +0 to every sum without any test.
+constexpr int INFO_UNUSED = 0xffff;
+constexpr double FAR_AWAY = 1.0e9;
 __device__ __forceinline__ int info_mol(int info) { return info & 0xffff; }
 __device__ __forceinline__ bool info_valid(int info) { return (info & 0xffff) != INFO_UNUSED; }
 __device__ __forceinline__ int info_type(int info) { return (info >> 16) & 0xff; }
 __device__ __forceinline__ int info_atom(int info) { return (info >> 24) & 0x1f; }
 __device__ __forceinline__ int info_lj(int info) { return (info >> 29) & 1; }
+__device__ __forceinline__ int info_col(int info) { return (info >> 12) & 0xff0; }   // type * sizeof(double2)
 
 // ---- the pair potential --------------------------------------------------------------------
 // Atom.java:102-103: (kTimesQ*q/r) + A*exp(-1*B*r) - (C/pow(r,6)) + (D/pow(r,12)).  Evaluated
@@ -58,6 +84,8 @@ __device__ __forceinline__ int info_lj(int info) { return (info >> 29) & 1; }
 // is FP64; the result differs from the reference's pow/sqrt/divide form by a few ulp per term
 // (bar: 1e-12 relative).  MODE 0: Coulomb only (C = D = A = 0 for the whole slot), 12 FP64
 // instructions; MODE 1: + Lennard-Jones, 17; MODE 2: + Born-Mayer exp.
+// `off` is 0 for a pair that counts and 1 for one that does not (own particle, empty slot):
+// with kqq = 0 and zero table entries the latter adds exactly +0 and never sees r = 0.
 __device__ __forceinline__ double rsqrt_f64(double r2)
 {
     double y;
@@ -70,9 +98,10 @@ __device__ __forceinline__ double rsqrt_f64(double r2)
 }
 
 template <int MODE>
-__device__ __forceinline__ double pair_accumulate(double acc, double dx, double dy, double dz, double kqq, double2 cd, double2 ab)
+__device__ __forceinline__ double pair_accumulate(double acc, double dx, double dy, double dz, double off, double kqq,
+                                                  double2 cd, double2 ab)
 {
-    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    const double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, off)));
     const double ri = rsqrt_f64(r2);
     double e = fma(kqq, ri, acc);
     if (MODE >= 1) {
@@ -86,25 +115,27 @@ __device__ __forceinline__ double pair_accumulate(double acc, double dx, double 
 
 // ---- team primitives -------------------------------------------------------------------------
 
-template <int W>
-__device__ __forceinline__ void team_sync()
+template <int L, int W>
+__device__ __forceinline__ unsigned team_mask()
 {
-    if (W == 1) __syncwarp(); else __syncthreads();
+    if (W > 1 || L == 32) return 0xffffffffu;
+    constexpr unsigned lanes = (L >= 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);
+    return lanes << ((threadIdx.x & 31) & ~(L - 1));
 }
 
-__device__ __forceinline__ double warp_sum(double v)
+template <int L, int W>
+__device__ __forceinline__ void team_sync(unsigned mask)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    if (W == 1) __syncwarp(mask); else __syncthreads();
 }
 
 // Sum over the team; every thread gets bitwise the same result.  `part` holds W doubles and
 // may be reused only after another team barrier.
-template <int W>
-__device__ __forceinline__ double team_sum(double a, double *part, int warp, int lane)
+template <int L, int W>
+__device__ __forceinline__ double team_sum(double a, double *part, int warp, int lane, unsigned mask)
 {
-    a = warp_sum(a);
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
     if (W > 1) {
         if (lane == 0) part[warp] = a;
         __syncthreads();
@@ -116,188 +147,194 @@ __device__ __forceinline__ double team_sum(double a, double *part, int warp, int
     return a;
 }
 
+template <int L, int W>
+__device__ __forceinline__ bool team_any(bool p, unsigned mask)
+{
+    if (W > 1) return __syncthreads_or(p) != 0;
+    return __ballot_sync(mask, p) != 0u;
+}
+
+// ---- shared-memory layout ----------------------------------------------------------------------
+// block: [cd (T x (T+1) double2, last column zero)] [ab (same, only with a Born-Mayer term)]
+//        [mol_off (N+1 int)] [moveable (n_moveable int)] [site_pos (S int)] [pos_info (n_pos int)]
+// then CPB x { ChainSmem, com (N x 3 double), sites (n_pos SiteRec) }
+
+__host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
+
+__host__ __device__ inline int smem_tables_bytes(int n_mol, int n_moveable, int n_types, bool has_exp, int n_sites, int n_pos)
+{
+    const int tab = n_types * (n_types + 1) * 16;
+    return tab * (has_exp ? 2 : 1) + align16((n_mol + 1) * 4) + align16(n_moveable * 4) + align16(n_sites * 4) + align16(n_pos * 4);
+}
+
+__host__ __device__ inline int smem_chain_bytes(int n_mol, int n_pos)
+{
+    return (int)sizeof(ChainSmem) + align16(n_mol * 24) + n_pos * (int)sizeof(SiteRec);
+}
+
+struct SmemTables {
+    const unsigned char *cd;     // byte-addressed: row offset + column offset
+    const unsigned char *ab;
+    const int *mol_off;
+    const int *moveable;
+    const int *site_pos;
+    const int *pos_info;
+};
+
+__device__ __forceinline__ SmemTables carve_tables(unsigned char *base, const DevSystem &sys)
+{
+    SmemTables t;
+    const int tab = sys.n_types * sys.row_stride;
+    t.cd = base;
+    t.ab = base + (sys.has_exp ? tab : 0);
+    unsigned char *p = base + tab * (sys.has_exp ? 2 : 1);
+    t.mol_off = (const int *)p;  p += align16((sys.n_mol + 1) * 4);
+    t.moveable = (const int *)p; p += align16(sys.n_moveable * 4);
+    t.site_pos = (const int *)p; p += align16(sys.n_sites * 4);
+    t.pos_info = (const int *)p;
+    return t;
+}
+
+__device__ __forceinline__ void load_tables(unsigned char *base, const DevSystem &sys)
+{
+    const int T = sys.n_types, tab = T * (T + 1) * 16;
+    double2 *cd = (double2 *)base, *ab = (double2 *)(base + tab);
+    for (int i = threadIdx.x; i < T * (T + 1); i += blockDim.x) {
+        const int r = i / (T + 1), c = i % (T + 1);
+        cd[i] = (c < T) ? sys.pair_cd[r * T + c] : make_double2(0.0, 0.0);
+        if (sys.has_exp) ab[i] = (c < T) ? sys.pair_ab[r * T + c] : make_double2(0.0, 0.0);
+    }
+    unsigned char *p = base + tab * (sys.has_exp ? 2 : 1);
+    int *mol_off = (int *)p;  p += align16((sys.n_mol + 1) * 4);
+    int *moveable = (int *)p; p += align16(sys.n_moveable * 4);
+    int *site_pos = (int *)p; p += align16(sys.n_sites * 4);
+    int *pos_info = (int *)p;
+    for (int i = threadIdx.x; i <= sys.n_mol; i += blockDim.x) mol_off[i] = sys.mol_off[i];
+    for (int i = threadIdx.x; i < sys.n_moveable; i += blockDim.x) moveable[i] = sys.moveable[i];
+    for (int i = threadIdx.x; i < sys.n_sites; i += blockDim.x) site_pos[i] = sys.site_pos[i];
+    for (int i = threadIdx.x; i < sys.n_pos; i += blockDim.x) pos_info[i] = sys.pos_info[i];
+}
+
+__device__ __forceinline__ double *chain_com(ChainSmem *cs) { return (double *)(cs + 1); }
+__device__ __forceinline__ SiteRec *chain_sites(ChainSmem *cs, const DevSystem &sys)
+{
+    return (SiteRec *)((unsigned char *)(cs + 1) + align16(sys.n_mol * 24));
+}
+
 // ---- energies ----------------------------------------------------------------------------------
 
+// One staged site against all SPL positions of this thread: straight-line code, 2*SPL independent
+// pair evaluations for the scheduler to interleave.  LJN = how many leading slots take the
+// Lennard-Jones form (compile time); the rest are Coulomb-only.
+template <int SPL, int LJN, int MODE_LJ>
+__device__ __forceinline__ void stage_site_energy(const StageSite &st, const unsigned char *tab_cd, const unsigned char *tab_ab,
+                                                  const double (&x)[SPL], const double (&y)[SPL], const double (&z)[SPL],
+                                                  const double (&qm)[SPL], const double (&off)[SPL], const int (&col)[SPL],
+                                                  double &eS, double &eE)
+{
+    double s[SPL], e[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; k++) {
+        const double kqq = st.kq * qm[k];                // kTimesQ * atom.q
+        const double ox = x[k] - st.ox, oy = y[k] - st.oy, oz = z[k] - st.oz;
+        const double nx = x[k] - st.nx, ny = y[k] - st.ny, nz = z[k] - st.nz;
+        const double2 z2 = make_double2(0.0, 0.0);
+        if (k < LJN) {
+            const double2 cd = *(const double2 *)(tab_cd + st.row + col[k]);
+            double2 ab = z2;
+            if (MODE_LJ == 2) ab = *(const double2 *)(tab_ab + st.row + col[k]);
+            s[k] = pair_accumulate<MODE_LJ>(0.0, ox, oy, oz, off[k], kqq, cd, ab);
+            e[k] = pair_accumulate<MODE_LJ>(0.0, nx, ny, nz, off[k], kqq, cd, ab);
+        } else {
+            s[k] = pair_accumulate<0>(0.0, ox, oy, oz, off[k], kqq, z2, z2);
+            e[k] = pair_accumulate<0>(0.0, nx, ny, nz, off[k], kqq, z2, z2);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SPL; k++) { eS += s[k]; eE += e[k]; }
+}
+
 // Per-thread partial sums of eStart / eEnd (Space.java:711-718) for the particle staged in
-// `stage` (sm sites, index m).  Pairs with the thread's unused slots or with sites of m itself
-// are computed and discarded (no divergence; a self pair gives NaN before the select).
-template <int SPL, bool HAS_EXP>
-__device__ __forceinline__ void move_energy(const SiteRegs<SPL> &R, const StageSite *stage, int sm, int m,
-                                            const double2 *s_cd, const double2 *s_ab, int T, int lj_slots,
+// cs->stage (sm sites, index m).  `mine` = this thread's first position record; slot k is at
+// mine[k * TPC]; info[k] its info word.  LJS = slots that may hold Lennard-Jones sites
+// (compile time, >= the system's actual count).
+template <int TPC, int SPL, int LJS, bool HAS_EXP>
+__device__ __forceinline__ void move_energy(const SiteRec *mine, const int (&info)[SPL], const ChainSmem *cs, int sm, int m,
+                                            const unsigned char *tab_cd, const unsigned char *tab_ab, int zero_col,
                                             double &eS, double &eE)
 {
     eS = 0.0; eE = 0.0;
-    bool on[SPL];
+    double x[SPL], y[SPL], z[SPL], qm[SPL], off[SPL];
+    int col[SPL];
 #pragma unroll
-    for (int k = 0; k < SPL; k++) on[k] = info_valid(R.info[k]) && info_mol(R.info[k]) != m;
+    for (int k = 0; k < SPL; k++) {
+        const SiteRec r = mine[k * TPC];
+        const bool on = info_mol(info[k]) != m;
+        x[k] = r.x; y[k] = r.y; z[k] = r.z;
+        qm[k] = on ? r.q : 0.0;
+        off[k] = on ? 0.0 : 1.0;
+        col[k] = on ? info_col(info[k]) : zero_col;
+    }
     for (int a = 0; a < sm; a++) {
-        const StageSite st = stage[a];
-        const double2 *row_cd = s_cd + st.type * T;
-#pragma unroll
-        for (int k = 0; k < SPL; k++) {
-            const double kqq = st.kq * R.q[k];               // kTimesQ * atom.q
-            const double ox = R.x[k] - st.ox, oy = R.y[k] - st.oy, oz = R.z[k] - st.oz;
-            const double nx = R.x[k] - st.nx, ny = R.y[k] - st.ny, nz = R.z[k] - st.nz;
-            double s, e;
-            if (HAS_EXP) {
-                const int tj = info_type(R.info[k]);
-                const double2 cd = row_cd[tj], ab = s_ab[st.type * T + tj];
-                s = pair_accumulate<2>(eS, ox, oy, oz, kqq, cd, ab);
-                e = pair_accumulate<2>(eE, nx, ny, nz, kqq, cd, ab);
-            } else if (k < lj_slots && st.lj) {
-                const double2 cd = row_cd[info_type(R.info[k])], z2 = make_double2(0.0, 0.0);
-                s = pair_accumulate<1>(eS, ox, oy, oz, kqq, cd, z2);
-                e = pair_accumulate<1>(eE, nx, ny, nz, kqq, cd, z2);
-            } else {
-                const double2 z2 = make_double2(0.0, 0.0);
-                s = pair_accumulate<0>(eS, ox, oy, oz, kqq, z2, z2);
-                e = pair_accumulate<0>(eE, nx, ny, nz, kqq, z2, z2);
-            }
-            eS = on[k] ? s : eS;
-            eE = on[k] ? e : eE;
-        }
+        const StageSite st = cs->stage[a];
+        if (HAS_EXP) stage_site_energy<SPL, SPL, 2>(st, tab_cd, tab_ab, x, y, z, qm, off, col, eS, eE);
+        else if (LJS > 0 && st.lj) stage_site_energy<SPL, LJS, 1>(st, tab_cd, tab_ab, x, y, z, qm, off, col, eS, eE);
+        else stage_site_energy<SPL, 0, 0>(st, tab_cd, tab_ab, x, y, z, qm, off, col, eS, eE);
     }
 }
 
 // Space.calcEnergy (Space.java:648-658): sum over particle pairs x < y of Molecule.calcEnergy(x -> y);
 // the site of the lower-indexed particle is `this` (its kTimesQ multiplies the other's q).
-// `scratch` must hold all S site coordinates in site order (written by the caller, team-synced).
-template <int SPL, int W, bool HAS_EXP>
-__device__ __forceinline__ double team_total_energy(const SiteRegs<SPL> &R, const double *scratch, const DevSystem &sys,
-                                                    const double2 *s_cd, const double2 *s_ab, double *part,
-                                                    int warp, int lane)
+template <int L, int W, int SPL, bool HAS_EXP>
+__device__ __forceinline__ double team_total_energy(const SiteRec *sites, const int (&info)[SPL], const DevSystem &sys,
+                                                    const SmemTables &tb, double *part, int tid, int warp, int lane, unsigned mask)
 {
+    constexpr int TPC = Team<L, W>::TPC;
     double acc = 0.0;
-    const int S = sys.n_sites, T = sys.n_types;
-    for (int i = 0; i < S; i++) {
-        const int infi = sys.site_info[i];
-        const int mi = info_mol(infi), ti = info_type(infi);
-        const double kqi = K_VALUE * sys.site_q[i];
-        const double xi = scratch[3 * i], yi = scratch[3 * i + 1], zi = scratch[3 * i + 2];
+    double x[SPL], y[SPL], z[SPL], q[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; k++) {
+        const SiteRec r = sites[tid + k * TPC];
+        x[k] = r.x; y[k] = r.y; z[k] = r.z; q[k] = r.q;
+    }
+    for (int p = 0; p < sys.n_pos; p++) {
+        const int infi = tb.pos_info[p];
+        if (!info_valid(infi)) continue;
+        const int mi = info_mol(infi), row = info_type(infi) * sys.row_stride;
+        const SiteRec ri = sites[p];
+        const double kqi = K_VALUE * ri.q;
 #pragma unroll
         for (int k = 0; k < SPL; k++) {
-            const int inf = R.info[k];
-            if (info_valid(inf) && mi < info_mol(inf)) {
-                const int tj = info_type(inf);
-                const double2 cd = s_cd[ti * T + tj];
+            if (info_valid(info[k]) && mi < info_mol(info[k])) {
+                const double2 cd = *(const double2 *)(tb.cd + row + info_col(info[k]));
                 double2 ab = make_double2(0.0, 0.0);
-                if (HAS_EXP) ab = s_ab[ti * T + tj];
-                acc = pair_accumulate<HAS_EXP ? 2 : 1>(acc, R.x[k] - xi, R.y[k] - yi, R.z[k] - zi, kqi * R.q[k], cd, ab);
+                if (HAS_EXP) ab = *(const double2 *)(tb.ab + row + info_col(info[k]));
+                acc = pair_accumulate<HAS_EXP ? 2 : 1>(acc, x[k] - ri.x, y[k] - ri.y, z[k] - ri.z, 0.0, kqi * q[k], cd, ab);
             }
         }
     }
-    return team_sum<W>(acc, part, warp, lane);
+    return team_sum<L, W>(acc, part, warp, lane, mask);
 }
 
-template <int SPL, int W>
-__device__ __forceinline__ void sites_to_scratch(const SiteRegs<SPL> &R, double *scratch, const int *pos_site, int tid)
+// global [S][3] (site order) <-> shared SiteRec[n_pos] (position order)
+template <int TPC>
+__device__ __forceinline__ void sites_to_global(const SiteRec *sites, double *dst, const DevSystem &sys, int tid)
 {
-#pragma unroll
-    for (int k = 0; k < SPL; k++) {
-        if (info_valid(R.info[k])) {
-            const int i = pos_site[tid + k * 32 * W];
-            scratch[3 * i] = R.x[k]; scratch[3 * i + 1] = R.y[k]; scratch[3 * i + 2] = R.z[k];
-        }
-    }
-    team_sync<W>();
-}
-
-template <int SPL, int W>
-__device__ __forceinline__ void sites_to_global(const SiteRegs<SPL> &R, double *dst, const int *pos_site, int tid)
-{
-#pragma unroll
-    for (int k = 0; k < SPL; k++) {
-        if (info_valid(R.info[k])) {
-            const int i = pos_site[tid + k * 32 * W];
-            dst[3 * i] = R.x[k]; dst[3 * i + 1] = R.y[k]; dst[3 * i + 2] = R.z[k];
-        }
+    for (int p = tid; p < sys.n_pos; p += TPC) {
+        const int i = sys.pos_site[p];
+        if (i >= 0) { const SiteRec r = sites[p]; dst[3 * i] = r.x; dst[3 * i + 1] = r.y; dst[3 * i + 2] = r.z; }
     }
 }
 
-template <int SPL, int W>
-__device__ __forceinline__ void sites_from_global(SiteRegs<SPL> &R, const double *src, const DevSystem &sys, int tid)
+template <int TPC>
+__device__ __forceinline__ void sites_from_global(SiteRec *sites, const double *src, const DevSystem &sys, int tid)
 {
-#pragma unroll
-    for (int k = 0; k < SPL; k++) {
-        const int i = sys.pos_site[tid + k * 32 * W];
-        if (i >= 0) {
-            R.x[k] = src[3 * i]; R.y[k] = src[3 * i + 1]; R.z[k] = src[3 * i + 2];
-            R.q[k] = sys.site_q[i];
-            R.info[k] = sys.site_info[i];
-        } else {
-            R.x[k] = R.y[k] = R.z[k] = 0.0; R.q[k] = 0.0; R.info[k] = INFO_UNUSED;
-        }
-    }
-}
-
-// ---- shared-memory carving -------------------------------------------------------------------
-
-struct SmemTables {
-    int *mol_off;
-    int *moveable;
-    double2 *cd;
-    double2 *ab;
-};
-
-struct SmemChain {
-    StageSite *stage;     // [TR_MAX_MOL_SITES]
-    ChainCtrl *ctrl;
-    uint32_t *ring;       // [3][MT_RING]
-    double *com;          // [N*3]
-    double *scratch;      // [S*3]
-    double *part;         // [W]
-    MoveDesc *desc;
-    int *flag;
-};
-
-__host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
-
-__host__ __device__ inline int smem_tables_bytes(int n_mol, int n_moveable, int n_types, bool has_exp)
-{
-    int b = align16((n_mol + 1) * 4) + align16(n_moveable * 4) + n_types * n_types * 16;
-    if (has_exp) b += n_types * n_types * 16;
-    return align16(b);
-}
-
-__host__ __device__ inline int smem_chain_bytes(int n_mol, int n_sites, int W)
-{
-    return align16(TR_MAX_MOL_SITES * (int)sizeof(StageSite)) + align16((int)sizeof(ChainCtrl)) + 3 * MT_RING * 4 +
-           align16(n_mol * 24) + align16(n_sites * 24) + align16(W * 8) + align16((int)sizeof(MoveDesc)) + 16;
-}
-
-__device__ __forceinline__ SmemTables carve_tables(unsigned char *base, const DevSystem &sys)
-{
-    SmemTables t;
-    unsigned char *p = base;
-    t.mol_off = (int *)p;  p += align16((sys.n_mol + 1) * 4);
-    t.moveable = (int *)p; p += align16(sys.n_moveable * 4);
-    t.cd = (double2 *)p;   p += sys.n_types * sys.n_types * 16;
-    t.ab = (double2 *)p;
-    return t;
-}
-
-__device__ __forceinline__ SmemChain carve_chain(unsigned char *p, const DevSystem &sys, int W)
-{
-    SmemChain c;
-    c.stage = (StageSite *)p;  p += align16(TR_MAX_MOL_SITES * (int)sizeof(StageSite));
-    c.ctrl = (ChainCtrl *)p;   p += align16((int)sizeof(ChainCtrl));
-    c.ring = (uint32_t *)p;    p += 3 * MT_RING * 4;
-    c.com = (double *)p;       p += align16(sys.n_mol * 24);
-    c.scratch = (double *)p;   p += align16(sys.n_sites * 24);
-    c.part = (double *)p;      p += align16(W * 8);
-    c.desc = (MoveDesc *)p;    p += align16((int)sizeof(MoveDesc));
-    c.flag = (int *)p;
-    return c;
-}
-
-__device__ __forceinline__ void load_tables(const SmemTables &t, const DevSystem &sys, bool has_exp)
-{
-    for (int i = threadIdx.x; i <= sys.n_mol; i += blockDim.x) t.mol_off[i] = sys.mol_off[i];
-    for (int i = threadIdx.x; i < sys.n_moveable; i += blockDim.x) t.moveable[i] = sys.moveable[i];
-    const int TT = sys.n_types * sys.n_types;
-    for (int i = threadIdx.x; i < TT; i += blockDim.x) {
-        t.cd[i] = sys.pair_cd[i];
-        if (has_exp) t.ab[i] = sys.pair_ab[i];
+    for (int p = tid; p < sys.n_pos; p += TPC) {
+        const int i = sys.pos_site[p];
+        SiteRec r;
+        if (i >= 0) { r.x = src[3 * i]; r.y = src[3 * i + 1]; r.z = src[3 * i + 2]; r.q = sys.site_q[i]; }
+        else { r.x = r.y = r.z = FAR_AWAY; r.q = 0.0; }
+        sites[p] = r;
     }
 }
 
@@ -305,13 +342,17 @@ __device__ __forceinline__ void load_tables(const SmemTables &t, const DevSystem
 
 // write(n) (Space.java:550-623 as far as the device is concerned): calcEnergy, keep the
 // structure, track the minimum (Space.java:614-617).
-template <int SPL, int W, bool HAS_EXP>
-__device__ __noinline__ double snapshot(const KParams &P, long long chain, const SiteRegs<SPL> R, const SmemChain sc,
-                                        const SmemTables tb, int n, int tid, int warp, int lane)
+template <int L, int W, int SPL, bool HAS_EXP>
+__device__ __noinline__ double snapshot(const KParams &P, long long chain, ChainSmem *cs, const SmemTables tb, int n,
+                                        int tid, int warp, int lane, unsigned mask)
 {
-    sites_to_scratch<SPL, W>(R, sc.scratch, P.sys.pos_site, tid);
-    const double e = team_total_energy<SPL, W, HAS_EXP>(R, sc.scratch, P.sys, tb.cd, tb.ab, sc.part, warp, lane);
-    ChainCtrl *c = sc.ctrl;
+    constexpr int TPC = Team<L, W>::TPC;
+    const SiteRec *sites = chain_sites(cs, P.sys);
+    int info[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
+    const double e = team_total_energy<L, W, SPL, HAS_EXP>(sites, info, P.sys, tb, cs->part, tid, warp, lane, mask);
+    ChainCtrl *c = &cs->ctrl;
     const int k = c->n_snaps;
     if (k < P.max_snaps) {
         if (tid == 0) {
@@ -319,25 +360,34 @@ __device__ __noinline__ double snapshot(const KParams &P, long long chain, const
             P.snap_tooth[chain * P.max_snaps + k] = n;
         }
         if (P.snap_sites)
-            sites_to_global<SPL, W>(R, P.snap_sites + ((size_t)chain * P.max_snaps + k) * (size_t)P.sys.n_sites * 3,
-                                    P.sys.pos_site, tid);
+            sites_to_global<TPC>(sites, P.snap_sites + ((size_t)chain * P.max_snaps + k) * (size_t)P.sys.n_sites * 3, P.sys, tid);
     }
-    team_sync<W>();
+    team_sync<L, W>(mask);
     if (tid == 0) {
         c->n_snaps = k + 1;
         if (e < c->min_energy) { c->min_energy = e; c->min_tooth = n; }
     }
-    team_sync<W>();
+    team_sync<L, W>(mask);
     return e;
+}
+
+__device__ __forceinline__ void refresh_derived(ChainSmem *cs)
+{
+    cs->thr_rot = double_threshold52(cs->ctrl.probRot);
+    cs->thr_trans = double_threshold52(cs->ctrl.probTrans);
+    cs->bound_hi = cs->ctrl.space_len * 0.75;    // Space.java:663,706; the lower bound spaceLen * -0.75 is its exact negative
 }
 
 // End of a point (Main.java:225-240) and, when it was the last one, end of the tooth (:242-257).
 // Returns true when the chain has finished.  Rare (once per movePerPt moves): kept out of line.
-template <int SPL, int W, bool HAS_EXP>
-__device__ __noinline__ bool end_of_point(const KParams &P, long long chain, const SiteRegs<SPL> R, const SmemChain sc,
-                                          const SmemTables tb, const tr_schedule &sch, int numTeeth, int tid, int warp, int lane)
+template <int L, int W, int SPL, bool HAS_EXP>
+__device__ __noinline__ bool end_of_point(const KParams &P, long long chain, ChainSmem *cs, const SmemTables tb,
+                                          int tid, int warp, int lane, unsigned mask)
 {
-    ChainCtrl *c = sc.ctrl;
+    constexpr int TPC = Team<L, W>::TPC;
+    ChainCtrl *c = &cs->ctrl;
+    const tr_schedule &sch = P.sched[c->sched];
+    const int numTeeth = sch.static_temp ? 1 : sch.num_teeth;   // Main.java:74-76
     const double t = c->t;
     {
         const int pi = c->n_points;
@@ -350,8 +400,10 @@ __device__ __noinline__ bool end_of_point(const KParams &P, long long chain, con
         }
         double me = __longlong_as_double(0x7ff8000000000000LL);
         if (movie && P.points) {
-            sites_to_scratch<SPL, W>(R, sc.scratch, P.sys.pos_site, tid);
-            me = team_total_energy<SPL, W, HAS_EXP>(R, sc.scratch, P.sys, tb.cd, tb.ab, sc.part, warp, lane);
+            int info[SPL];
+#pragma unroll
+            for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
+            me = team_total_energy<L, W, SPL, HAS_EXP>(chain_sites(cs, P.sys), info, P.sys, tb, cs->part, tid, warp, lane, mask);
         }
         if (tid == 0) {
             if (P.points && pi < P.max_points) {
@@ -366,7 +418,7 @@ __device__ __noinline__ bool end_of_point(const KParams &P, long long chain, con
             c->y += 1; c->z = 0;
             c->totalE = 0.0; c->totalSqE = 0.0;
         }
-        team_sync<W>();
+        team_sync<L, W>(mask);
     }
     if (c->y < c->ptsPerTooth) return false;
 
@@ -382,6 +434,7 @@ __device__ __noinline__ bool end_of_point(const KParams &P, long long chain, con
             c->maxD = __ddiv_rn(c->maxD, 100.0);
             c->maxRot = __ddiv_rn(c->maxRot, 100.0);
             c->probRot = 0.0; c->probTrans = 0.0;
+            refresh_derived(cs);
             // x-- then x++: the finale repeats the same tooth index
         } else {
             c->x = x + 1;
@@ -389,12 +442,12 @@ __device__ __noinline__ bool end_of_point(const KParams &P, long long chain, con
         c->y = 0; c->accepted = 0; c->total = 0;
         c->delT = c->t / (double)(c->ptsPerTooth - 1);
     }
-    team_sync<W>();
+    team_sync<L, W>(mask);
     if (!start_finale) {
-        snapshot<SPL, W, HAS_EXP>(P, chain, R, sc, tb, x + 1, tid, warp, lane);   // write(x+1)
+        snapshot<L, W, SPL, HAS_EXP>(P, chain, cs, tb, x + 1, tid, warp, lane, mask);   // write(x+1)
         if (c->x >= numTeeth) {
             if (tid == 0) c->done = 1;
-            team_sync<W>();
+            team_sync<L, W>(mask);
             return true;
         }
     }
@@ -403,68 +456,70 @@ __device__ __noinline__ bool end_of_point(const KParams &P, long long chain, con
 
 // ---- the kernel ------------------------------------------------------------------------------
 
-template <int W> struct LaunchCfg { static constexpr int CPB = (W == 1) ? 4 : 1; };
-
-template <int SPL, int W, bool HAS_EXP, bool TRACE, int MINB>
-__global__ void __launch_bounds__(32 * W * LaunchCfg<W>::CPB, MINB) anneal_kernel(const __grid_constant__ KParams P)
+template <int L, int W, int SPL, int LJS, bool HAS_EXP, bool TRACE, int MINB>
+__global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const __grid_constant__ KParams P)
 {
-    constexpr int CPB = LaunchCfg<W>::CPB;
-    constexpr int TPC = 32 * W;
+    constexpr int TPC = Team<L, W>::TPC;
+    constexpr int CPB = Team<L, W>::CPB;
     extern __shared__ __align__(16) unsigned char smem[];
     const DevSystem &sys = P.sys;
+    load_tables(smem, sys);
     const SmemTables tb = carve_tables(smem, sys);
-    load_tables(tb, sys, HAS_EXP);
 
     const int lane = threadIdx.x & 31;
-    const int warp_in_block = threadIdx.x >> 5;
-    const int team = (W == 1) ? warp_in_block : 0;
-    const int warp = (W == 1) ? 0 : warp_in_block;          // warp index inside the team
-    const int tid = (W == 1) ? lane : (int)threadIdx.x;     // thread index inside the team
+    const int team = (W == 1) ? (int)threadIdx.x / TPC : 0;
+    const int warp = (W == 1) ? 0 : (int)threadIdx.x >> 5;            // warp index inside the team
+    const int tid = (W == 1) ? (int)threadIdx.x % TPC : (int)threadIdx.x;   // thread index inside the team
+    const unsigned mask = team_mask<L, W>();
     const long long chain = (long long)blockIdx.x * CPB + team;
-    const SmemChain sc = carve_chain(smem + P.smem_tables + team * P.smem_per_chain, sys, W);
+    ChainSmem *cs = (ChainSmem *)(smem + P.smem_tables + team * P.smem_per_chain);
+    double *com = chain_com(cs);
+    SiteRec *sites = chain_sites(cs, sys);
     const bool active = chain < P.n_chains;
     const long long ch = active ? chain : 0;                 // idle teams shadow chain 0 read-only
 
-    // chain state -> shared memory / registers
-    ChainCtrl *c = sc.ctrl;
+    // chain state -> shared memory
+    ChainCtrl *c = &cs->ctrl;
     {
         const int *src = (const int *)(P.ctrl + ch);
         int *dst = (int *)c;
         for (int i = tid; i < (int)(sizeof(ChainCtrl) / 4); i += TPC) dst[i] = src[i];
-        const double *cs = P.com + (size_t)ch * sys.n_mol * 3;
-        for (int i = tid; i < sys.n_mol * 3; i += TPC) sc.com[i] = cs[i];
+        const double *cg = P.com + (size_t)ch * sys.n_mol * 3;
+        for (int i = tid; i < sys.n_mol * 3; i += TPC) com[i] = cg[i];
+        sites_from_global<TPC>(sites, P.sites + (size_t)ch * sys.n_sites * 3, sys, tid);
     }
-    SiteRegs<SPL> R;
-    sites_from_global<SPL, W>(R, P.sites + (size_t)ch * sys.n_sites * 3, sys, tid);
     __syncthreads();
+    if (tid == 0) refresh_derived(cs);
+    team_sync<L, W>(mask);
     if (!active || c->done) return;     // whole teams leave together (W > 1: the whole block)
 
-    const tr_schedule &sch = P.sched[c->sched];   // global (L1-resident, uniform): fields are re-read on use
-    const int S = sys.n_sites, T = sys.n_types;
-    const int lj_slots = (sys.n_lj_pos + TPC - 1) / TPC;
+    const tr_schedule &sch = P.sched[c->sched];   // global (L1-resident, team-uniform): fields are re-read on use
+    const int S = sys.n_sites;
     const FastMod three = fastmod_make(3);
+    const SiteRec *mine = sites + tid;            // this thread's positions: mine[k * TPC]
+    const unsigned char *tab_cd = smem;           // pair tables sit at the start of dynamic shared memory
+    const unsigned char *tab_ab = smem + (sys.has_exp ? sys.n_types * sys.row_stride : 0);
+    int info[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
     MtRing gM, gS, gR;
     {
         uint32_t *mt = P.mt + (size_t)chain * 3 * 2 * MT_N;
-        mt_ring_open(gM, mt + STREAM_M * 2 * MT_N, sc.ring + STREAM_M * MT_RING, &c->rng[STREAM_M]);
-        mt_ring_open(gS, mt + STREAM_S * 2 * MT_N, sc.ring + STREAM_S * MT_RING, &c->rng[STREAM_S]);
-        mt_ring_open(gR, mt + STREAM_R * 2 * MT_N, sc.ring + STREAM_R * MT_RING, &c->rng[STREAM_R]);
+        mt_ring_open(gM, mt + STREAM_M * 2 * MT_N, cs->ring[STREAM_M], &c->rng[STREAM_M]);
+        mt_ring_open(gS, mt + STREAM_S * 2 * MT_N, cs->ring[STREAM_S], &c->rng[STREAM_S]);
+        mt_ring_open(gR, mt + STREAM_R * 2 * MT_N, cs->ring[STREAM_R], &c->rng[STREAM_R]);
     }
-
-    const int numTeeth = sch.static_temp ? 1 : sch.num_teeth;   // Main.java:74-76
-    const double bound_hi = c->space_len * 0.75;                // Space.java:663,706
-    const double bound_lo = c->space_len * -0.75;
 
     // Main.java:64,71: write(0) and startingEnergy = calcEnergy()
     if (!c->started) {
-        const double e0 = snapshot<SPL, W, HAS_EXP>(P, chain, R, sc, tb, 0, tid, warp, lane);
+        const double e0 = snapshot<L, W, SPL, HAS_EXP>(P, chain, cs, tb, 0, tid, warp, lane, mask);
         if (tid == 0) {
             c->start_energy = e0;
             c->running = e0;
             c->started = 1;
             c->delT = c->t / (double)(c->ptsPerTooth - 1);      // Main.java:188 for tooth 0
         }
-        team_sync<W>();
+        team_sync<L, W>(mask);
     }
 
     long long budget = P.max_moves > 0 ? P.max_moves : 0x7fffffffffffffffLL;
@@ -474,40 +529,41 @@ __global__ void __launch_bounds__(32 * W * LaunchCfg<W>::CPB, MINB) anneal_kerne
         int z = c->z;
         int nz = sch.moves_per_point - z;
         if ((long long)nz > budget) nz = (int)budget;
+        if (nz > (1 << 20)) nz = 1 << 20;         // keeps the 32-bit per-segment counters below in range
         const long long moves_before = c->moves;
         const double t = c->t;
-        // loop-carried statistics live in registers of every thread (uniform values)
+        // loop-carried statistics live in registers of every thread (team-uniform values)
         double running = c->running, totalE = c->totalE, totalSqE = c->totalSqE;
-        int accepted = 0;
-        int evaluated = 0;
-        long long pair_evals = 0;
+        int accepted = 0, evaluated = 0;
+        unsigned sum_sm = 0, sum_sm2 = 0;         // pair evaluations = 2 * (S * sum_sm - sum_sm2)
 
         for (int it = 0; it < nz; it++, z++) {
             // -- choose the move: Main.java:197-213 (warp 0 of the team owns the RNG)
             int m = 0, rot = 0, axis = -1, magwalk = 0;
             double va = 0.0, vb = 0.0, vc = 0.0;       // translation vector or (sin, cos)
             if (warp == 0) {
-                mt_ring_reserve(gS, 9, lane);          // pick + 3 doubles + Metropolis double
-                mt_ring_reserve(gM, 4, lane);          // two doubles, always (Main.java:199-208)
-                mt_ring_reserve(gR, 3, lane);          // angle double + axis
-                const int pick = mt_ring_next_int(gS, sys.pick_mod, lane);       // Space.java:736
+                mt_ring_reserve<L>(gS, 9, tid, mask);  // pick + 3 doubles + Metropolis double
+                mt_ring_reserve<L>(gM, 4, tid, mask);  // two doubles, always (Main.java:199-208)
+                mt_ring_reserve<L>(gR, 3, tid, mask);  // angle double + axis
+                const int pick = mt_ring_next_int<L>(gS, sys.pick_mod, tid, mask);   // Space.java:736
                 m = tb.moveable[pick];
                 const int sm0 = tb.mol_off[m + 1] - tb.mol_off[m];
-                const double u1 = mt_ring_next_double(gM);                       // Main.java:199
-                const double u2 = mt_ring_next_double(gM);                       // :200 or :208
-                rot = (u1 >= 0.5 && sm0 > 1) ? 1 : 0;
+                // r.nextDouble() >= 0.5 (Main.java:199): the top bit of the first word; both words are consumed
+                const unsigned long long u1 = mt_ring_next52(gM);
+                const unsigned long long u2 = mt_ring_next52(gM);                    // :200 or :208
+                rot = (u1 >= (1ull << 51) && sm0 > 1) ? 1 : 0;
                 if (rot) {
-                    magwalk = (u2 >= c->probRot) ? 0 : 1;
+                    magwalk = (u2 >= cs->thr_rot) ? 0 : 1;
                     const double maxR = magwalk ? JAVA_TWO_PI : c->maxRot;
-                    const double u = mt_ring_next_double(gR);                    // Molecule.java:67
+                    const double u = mt_ring_next_double(gR);                        // Molecule.java:67
                     const double rotAmount = __dmul_rn(__dmul_rn(__dsub_rn(u, 0.5), 2.0), maxR);
-                    axis = mt_ring_next_int(gR, three, lane);                    // Molecule.java:68
+                    axis = mt_ring_next_int<L>(gR, three, tid, mask);                // Molecule.java:68
                     sincos(rotAmount, &va, &vb);
                 } else {
-                    magwalk = (u2 >= c->probTrans) ? 0 : 1;
+                    magwalk = (u2 >= cs->thr_trans) ? 0 : 1;
                     const double maxD = c->maxD;
                     const double maxT = magwalk ? __dmul_rn(maxD, sch.magwalk_factor_trans) : maxD;
-                    const double ux = mt_ring_next_double(gS);                   // Space.java:694-696
+                    const double ux = mt_ring_next_double(gS);                       // Space.java:694-696
                     const double uy = mt_ring_next_double(gS);
                     const double uz = mt_ring_next_double(gS);
                     va = __dsub_rn(__dmul_rn(__dmul_rn(ux, 2.0), maxT), maxT);
@@ -516,83 +572,75 @@ __global__ void __launch_bounds__(32 * W * LaunchCfg<W>::CPB, MINB) anneal_kerne
                 }
                 if (W > 1 && lane == 0) {
                     MoveDesc d; d.a = va; d.b = vb; d.c = vc; d.m = m; d.rot = rot; d.axis = axis; d.magwalk = magwalk;
-                    *sc.desc = d;
+                    cs->desc = d;
                 }
             }
             if (W > 1) {
                 __syncthreads();
-                const MoveDesc d = *sc.desc;
+                const MoveDesc d = cs->desc;
                 va = d.a; vb = d.b; vc = d.c; m = d.m; rot = d.rot; axis = d.axis; magwalk = d.magwalk;
             }
-            const int sm = tb.mol_off[m + 1] - tb.mol_off[m];
+            const int off = tb.mol_off[m];
+            const int sm = tb.mol_off[m + 1] - off;
 
-            // -- trial geometry by the owners of m's sites; stage old + trial coordinates
+            // -- trial geometry: thread a < sm handles site a of m; stage old + trial coordinates
             bool oob = false;
-            if (rot) {
-                const double cx = sc.com[3 * m], cy = sc.com[3 * m + 1], cz = sc.com[3 * m + 2];
-                const double sn = va, cs = vb, nsn = __dmul_rn(-1.0, va);
-#pragma unroll
-                for (int k = 0; k < SPL; k++) {
-                    if (info_mol(R.info[k]) == m) {
-                        // Molecule.java:70-95, operation for operation, no contraction
-                        const double ax = __dsub_rn(R.x[k], cx), ay = __dsub_rn(R.y[k], cy), az = __dsub_rn(R.z[k], cz);
-                        double tx, ty, tz;
-                        if (axis == 0) {
-                            tx = ax;
-                            ty = __dadd_rn(__dmul_rn(cs, ay), __dmul_rn(sn, az));
-                            tz = __dadd_rn(__dmul_rn(nsn, ay), __dmul_rn(cs, az));
-                        } else if (axis == 1) {
-                            tx = __dsub_rn(__dmul_rn(cs, ax), __dmul_rn(sn, az));
-                            ty = ay;
-                            tz = __dadd_rn(__dmul_rn(sn, ax), __dmul_rn(cs, az));
-                        } else {
-                            tx = __dadd_rn(__dmul_rn(cs, ax), __dmul_rn(sn, ay));
-                            ty = __dadd_rn(__dmul_rn(nsn, ax), __dmul_rn(cs, ay));
-                            tz = az;
-                        }
-                        R.x[k] = __dadd_rn(ax, cx); R.y[k] = __dadd_rn(ay, cy); R.z[k] = __dadd_rn(az, cz);
-                        tx = __dadd_rn(tx, cx); ty = __dadd_rn(ty, cy); tz = __dadd_rn(tz, cz);
-                        StageSite st;
-                        st.ox = R.x[k]; st.oy = R.y[k]; st.oz = R.z[k];
-                        st.nx = tx; st.ny = ty; st.nz = tz;
-                        st.kq = __dmul_rn(K_VALUE, R.q[k]);
-                        st.type = info_type(R.info[k]); st.lj = info_lj(R.info[k]);
-                        sc.stage[info_atom(R.info[k])] = st;
-                        oob |= (tx > bound_hi) | (tx < bound_lo) | (ty > bound_hi) | (ty < bound_lo) | (tz > bound_hi) | (tz < bound_lo);
+            int my_pos = 0;
+            if (tid < sm) {
+                my_pos = tb.site_pos[off + tid];
+                const SiteRec r = sites[my_pos];
+                const int inf = tb.pos_info[my_pos];
+                double ox = r.x, oy = r.y, oz = r.z, tx, ty, tz;
+                if (rot) {
+                    // Molecule.java:70-95, operation for operation, no contraction (va = sin, vb = cos)
+                    const double cx = com[3 * m], cy = com[3 * m + 1], cz = com[3 * m + 2];
+                    const double nsn = __dmul_rn(-1.0, va);
+                    const double ax = __dsub_rn(ox, cx), ay = __dsub_rn(oy, cy), az = __dsub_rn(oz, cz);
+                    if (axis == 0) {
+                        tx = ax;
+                        ty = __dadd_rn(__dmul_rn(vb, ay), __dmul_rn(va, az));
+                        tz = __dadd_rn(__dmul_rn(nsn, ay), __dmul_rn(vb, az));
+                    } else if (axis == 1) {
+                        tx = __dsub_rn(__dmul_rn(vb, ax), __dmul_rn(va, az));
+                        ty = ay;
+                        tz = __dadd_rn(__dmul_rn(va, ax), __dmul_rn(vb, az));
+                    } else {
+                        tx = __dadd_rn(__dmul_rn(vb, ax), __dmul_rn(va, ay));
+                        ty = __dadd_rn(__dmul_rn(nsn, ax), __dmul_rn(vb, ay));
+                        tz = az;
                     }
+                    // a.x += x: the committed coordinate keeps the (a.x - x) + x round trip even if the move is rejected
+                    ox = __dadd_rn(ax, cx); oy = __dadd_rn(ay, cy); oz = __dadd_rn(az, cz);
+                    sites[my_pos].x = ox; sites[my_pos].y = oy; sites[my_pos].z = oz;
+                    tx = __dadd_rn(tx, cx); ty = __dadd_rn(ty, cy); tz = __dadd_rn(tz, cz);
+                } else {
+                    tx = __dadd_rn(ox, va); ty = __dadd_rn(oy, vb); tz = __dadd_rn(oz, vc);
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < SPL; k++) {
-                    if (info_mol(R.info[k]) == m) {
-                        const double tx = __dadd_rn(R.x[k], va), ty = __dadd_rn(R.y[k], vb), tz = __dadd_rn(R.z[k], vc);
-                        StageSite st;
-                        st.ox = R.x[k]; st.oy = R.y[k]; st.oz = R.z[k];
-                        st.nx = tx; st.ny = ty; st.nz = tz;
-                        st.kq = __dmul_rn(K_VALUE, R.q[k]);
-                        st.type = info_type(R.info[k]); st.lj = info_lj(R.info[k]);
-                        sc.stage[info_atom(R.info[k])] = st;
-                        oob |= (tx > bound_hi) | (tx < bound_lo) | (ty > bound_hi) | (ty < bound_lo) | (tz > bound_hi) | (tz < bound_lo);
-                    }
-                }
+                StageSite st;
+                st.ox = ox; st.oy = oy; st.oz = oz;
+                st.nx = tx; st.ny = ty; st.nz = tz;
+                st.kq = __dmul_rn(K_VALUE, r.q);
+                st.row = info_type(inf) * sys.row_stride; st.lj = info_lj(inf);
+                cs->stage[tid] = st;
+                const double b = cs->bound_hi;      // Space.java:663,706: t > L*0.75 || t < L*-0.75
+                oob = (fabs(tx) > b) | (fabs(ty) > b) | (fabs(tz) > b);
             }
-            int any_oob;
-            if (W == 1) { any_oob = __any_sync(0xffffffffu, oob); __syncwarp(); }
-            else any_oob = __syncthreads_or(oob);
+            const bool any_oob = team_any<L, W>(oob, mask);
+            if (W == 1) __syncwarp(mask);
 
             // -- energy, Metropolis, commit: Space.java:668-689 / :711-733
             int acc = 0, drew = 0;
             double eS = 0.0, eE = 0.0, dE = 0.0, rnd = 0.0;
             if (!any_oob) {
-                move_energy<SPL, HAS_EXP>(R, sc.stage, sm, m, tb.cd, tb.ab, T, lj_slots, eS, eE);
+                move_energy<TPC, SPL, LJS, HAS_EXP>(mine, info, cs, sm, m, tab_cd, tab_ab, sys.zero_col, eS, eE);
                 // eEnd - eStart, differenced per thread before the reduction (less cancellation than
                 // reducing the two ~100x larger sums; the reference's own value carries the same rounding noise)
-                dE = team_sum<W>(eE - eS, sc.part, warp, lane);
+                dE = team_sum<L, W>(eE - eS, cs->part, warp, lane, mask);
                 if (TRACE) {
-                    team_sync<W>();
-                    eS = team_sum<W>(eS, sc.part, warp, lane);
-                    team_sync<W>();
-                    eE = team_sum<W>(eE, sc.part, warp, lane);
+                    team_sync<L, W>(mask);
+                    eS = team_sum<L, W>(eS, cs->part, warp, lane, mask);
+                    team_sync<L, W>(mask);
+                    eE = team_sum<L, W>(eE, cs->part, warp, lane, mask);
                 }
                 acc = 1;
                 if (dE > 0.0) {
@@ -603,29 +651,29 @@ __global__ void __launch_bounds__(32 * W * LaunchCfg<W>::CPB, MINB) anneal_kerne
                             const double test = exp(__ddiv_rn(__dmul_rn(-1.0, dE), __dmul_rn(BOLTZMANN_CONSTANT, t)));
                             if (rnd > test) acc = 0;
                         }
-                        if (W > 1 && lane == 0) { sc.flag[0] = acc; }
+                        if (W > 1 && lane == 0) cs->flag[0] = acc;
                     }
                     drew = 1;
-                    if (W > 1) { __syncthreads(); acc = sc.flag[0]; }
+                    if (W > 1) { __syncthreads(); acc = cs->flag[0]; }
                 }
                 if (acc) {
-#pragma unroll
-                    for (int k = 0; k < SPL; k++) {
-                        if (info_mol(R.info[k]) == m) {
-                            const StageSite *st = &sc.stage[info_atom(R.info[k])];
-                            R.x[k] = st->nx; R.y[k] = st->ny; R.z[k] = st->nz;
-                        }
+                    // every thread read its own positions before the reduction it just took part in, so m's
+                    // records can be overwritten now: setTemps (Molecule.java:128-135)
+                    if (tid < sm) {
+                        const StageSite *st = &cs->stage[tid];
+                        sites[my_pos].x = st->nx; sites[my_pos].y = st->ny; sites[my_pos].z = st->nz;
                     }
-                    if (!rot && tid == 0) {   // m.x = m.tempx (Molecule.java:129-131)
-                        sc.com[3 * m] = __dadd_rn(sc.com[3 * m], va);
-                        sc.com[3 * m + 1] = __dadd_rn(sc.com[3 * m + 1], vb);
-                        sc.com[3 * m + 2] = __dadd_rn(sc.com[3 * m + 2], vc);
+                    if (!rot && tid == 0) {   // m.x = m.tempx
+                        com[3 * m] = __dadd_rn(com[3 * m], va);
+                        com[3 * m + 1] = __dadd_rn(com[3 * m + 1], vb);
+                        com[3 * m + 2] = __dadd_rn(com[3 * m + 2], vc);
                     }
                 }
                 evaluated++;
-                pair_evals += 2LL * sm * (S - sm);
+                sum_sm += (unsigned)sm;
+                sum_sm2 += (unsigned)(sm * sm);
             }
-            team_sync<W>();   // stage / com / flag are free for the next move
+            team_sync<L, W>(mask);   // sites / stage / com / flag are settled for the next move
 
             // -- Main.java:215-223
             running = __dadd_rn(running, acc ? dE : 0.0);
@@ -654,28 +702,28 @@ __global__ void __launch_bounds__(32 * W * LaunchCfg<W>::CPB, MINB) anneal_kerne
             c->accepted_all += accepted;
             c->moves = moves_before + nz;
             c->evaluated += evaluated;
-            c->pair_evals += pair_evals;
+            c->pair_evals += 2LL * ((long long)S * sum_sm - sum_sm2);
         }
-        team_sync<W>();
-        if (z < sch.moves_per_point) break;       // budget exhausted inside a point
-        if (end_of_point<SPL, W, HAS_EXP>(P, chain, R, sc, tb, sch, numTeeth, tid, warp, lane)) break;
+        team_sync<L, W>(mask);
+        if (z < sch.moves_per_point) continue;    // budget exhausted (loop ends) or a capped segment (loop goes on)
+        if (end_of_point<L, W, SPL, HAS_EXP>(P, chain, cs, tb, tid, warp, lane, mask)) break;
     }
 
     // chain state -> global memory
     if (warp == 0) {
-        mt_ring_close(gM, lane);
-        mt_ring_close(gS, lane);
-        mt_ring_close(gR, lane);
+        mt_ring_close(gM, tid, mask);
+        mt_ring_close(gS, tid, mask);
+        mt_ring_close(gR, tid, mask);
     }
-    team_sync<W>();
+    team_sync<L, W>(mask);
     {
         int *dst = (int *)(P.ctrl + chain);
         const int *src = (const int *)c;
         for (int i = tid; i < (int)(sizeof(ChainCtrl) / 4); i += TPC) dst[i] = src[i];
-        double *cd = P.com + (size_t)chain * sys.n_mol * 3;
-        for (int i = tid; i < sys.n_mol * 3; i += TPC) cd[i] = sc.com[i];
+        double *cg = P.com + (size_t)chain * sys.n_mol * 3;
+        for (int i = tid; i < sys.n_mol * 3; i += TPC) cg[i] = com[i];
+        sites_to_global<TPC>(sites, P.sites + (size_t)chain * S * 3, sys, tid);
     }
-    sites_to_global<SPL, W>(R, P.sites + (size_t)chain * S * 3, sys.pos_site, tid);
 }
 
 }  // namespace tr

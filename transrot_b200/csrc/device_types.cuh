@@ -20,8 +20,11 @@ struct DevSystem {
     FastMod pick_mod;            // nextInt(n_moveable) without a divide
     const int *mol_off;          // [n_mol+1]
     const int *site_info;        // [n_sites]  mol | type << 16 | index-in-particle << 24
+    int row_stride;              // bytes per row of the shared-memory pair tables = (n_types + 1) * 16
+    int zero_col;                // byte offset of the all-zero column = n_types * 16
     const int *pos_site;         // [n_pos]    site held at each (thread, slot) position, or -1
-    const unsigned char *type_lj;// [n_types]  1 = type has a non-zero C or D with some type
+    const int *site_pos;         // [n_sites]  inverse of pos_site
+    const int *pos_info;         // [n_pos]    site_info of the site at each position; empty: mol = 0xffff, type = n_types
     const double *site_q;        // [n_sites]
     const double2 *pair_cd;      // [n_types*n_types] {C, D}
     const double2 *pair_ab;      // [n_types*n_types] {A, B}

@@ -117,12 +117,13 @@ struct MtCursor {
 
 #ifdef __CUDACC__
 
+// A stream as seen by its owning TEAM of L lanes (L = 16 or 32, all inside one warp).
 struct MtRing {
     uint32_t *mt;        // global: [2][624] ping-pong buffers of this stream
     uint32_t *ring;      // shared: [MT_RING] tempered words
     MtCursor *cur;       // shared: persistent cursor (inside the chain's ChainCtrl copy)
-    int rd;              // next ring slot to read          (warp-uniform)
-    int avail;           // unread words in the ring        (warp-uniform)
+    int rd;              // next ring slot to read          (team-uniform)
+    int avail;           // unread words in the ring        (team-uniform)
 };
 
 __device__ __forceinline__ void mt_ring_open(MtRing &g, uint32_t *mt, uint32_t *ring, MtCursor *cur)
@@ -130,43 +131,59 @@ __device__ __forceinline__ void mt_ring_open(MtRing &g, uint32_t *mt, uint32_t *
     g.mt = mt; g.ring = ring; g.cur = cur; g.rd = 0; g.avail = 0;
 }
 
-// Append the next <= 32 words of the stream to the ring (all lanes of the owning warp call this).
-// Block b+1 is generated from block b held in the other buffer, so the regeneration is exact
-// and a block stays readable until the one after next is started:
+// Append the next <= 32 words of the stream to the ring (all L lanes of the owning team call this;
+// tl = lane index inside the team, mask = the team's lanes).  Block b+1 is generated from block b
+// held in the other buffer, so the regeneration is exact and a block stays readable until the one
+// after next is started:
 //   new[k] = (k < 227 ? old[k+397] : new[k-227]) ^ twist(old[k], k == 623 ? new[0] : old[k+1]).
-__device__ __forceinline__ void mt_ring_refill(MtRing &g, int lane)
+// Words of one 32-word window never depend on each other (227 > 32), so L < 32 lanes may take
+// them in any order.
+template <int L>
+__device__ __noinline__ int mt_ring_refill_words(uint32_t *mt, uint32_t *ring, MtCursor *cur, int wr, int tl, unsigned mask)
 {
-    int par = g.cur->par, gen = g.cur->gen, fed = g.cur->fed;
-    __syncwarp();
+    int par = cur->par, gen = cur->gen, fed = cur->fed;
+    __syncwarp(mask);
     if (fed >= MT_N) { par ^= 1; gen = 0; fed = 0; }
-    uint32_t *B = g.mt + par * MT_N;
-    const uint32_t *O = g.mt + (par ^ 1) * MT_N;
-    const int limit = (fed < gen) ? gen : MT_N;      // load mode stops at the generated prefix
+    uint32_t *B = mt + par * MT_N;
+    const uint32_t *O = mt + (par ^ 1) * MT_N;
+    const bool load = fed < gen;
+    const int limit = load ? gen : MT_N;             // load mode stops at the generated prefix
     const int count = (limit - fed < 32) ? limit - fed : 32;
-    const int k = fed + lane;
-    uint32_t v = 0;
-    if (fed < gen) {
-        if (lane < count) v = B[k];
-    } else if (lane < count) {
-        const uint32_t a = O[k];
-        const uint32_t b = (k == MT_N - 1) ? B[0] : O[k + 1];
-        const uint32_t far = (k < MT_N - MT_M) ? O[k + MT_M] : B[k + MT_M - MT_N];
-        const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-        v = far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        B[k] = v;
+#pragma unroll
+    for (int i = tl; i < 32; i += L) {
+        if (i < count) {
+            const int k = fed + i;
+            uint32_t v;
+            if (load) v = B[k];
+            else {
+                const uint32_t a = O[k];
+                const uint32_t b = (k == MT_N - 1) ? B[0] : O[k + 1];
+                const uint32_t far = (k < MT_N - MT_M) ? O[k + MT_M] : B[k + MT_M - MT_N];
+                const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+                v = far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                B[k] = v;
+            }
+            ring[(wr + i) & (MT_RING - 1)] = mt_temper(v);
+        }
     }
-    if (fed >= gen) gen = fed + count;
-    if (lane < count) g.ring[(g.rd + g.avail + lane) & (MT_RING - 1)] = mt_temper(v);
+    if (!load) gen = fed + count;
     fed += count;
-    g.avail += count;
-    if (lane == 0) { g.cur->par = par; g.cur->gen = gen; g.cur->fed = fed; }
-    __syncwarp();
+    if (tl == 0) { cur->par = par; cur->gen = gen; cur->fed = fed; }
+    __syncwarp(mask);
+    return count;
+}
+
+template <int L>
+__device__ __forceinline__ void mt_ring_refill(MtRing &g, int tl, unsigned mask)
+{
+    g.avail += mt_ring_refill_words<L>(g.mt, g.ring, g.cur, g.rd + g.avail, tl, mask);
 }
 
 // Hoisted availability test: call once per move with the most words the move can draw.
-__device__ __forceinline__ void mt_ring_reserve(MtRing &g, int need, int lane)
+template <int L>
+__device__ __forceinline__ void mt_ring_reserve(MtRing &g, int need, int tl, unsigned mask)
 {
-    while (g.avail < need) mt_ring_refill(g, lane);
+    while (g.avail < need) mt_ring_refill<L>(g, tl, mask);
 }
 
 __device__ __forceinline__ uint32_t mt_ring_next32(MtRing &g)
@@ -177,12 +194,26 @@ __device__ __forceinline__ uint32_t mt_ring_next32(MtRing &g)
     return w;
 }
 
-// BitsStreamGenerator.nextDouble: (((long)next(26) << 26) | next(26)) * 0x1.0p-52
-__device__ __forceinline__ double mt_ring_next_double(MtRing &g)
+// The 52-bit integer of BitsStreamGenerator.nextDouble: ((long)next(26) << 26) | next(26)
+__device__ __forceinline__ unsigned long long mt_ring_next52(MtRing &g)
 {
     const uint32_t hi = mt_ring_next32(g) >> 6;
     const uint32_t lo = mt_ring_next32(g) >> 6;
-    return (double)(int64_t)(((uint64_t)hi << 26) | lo) * 0x1.0p-52;
+    return ((unsigned long long)hi << 26) | lo;
+}
+
+// BitsStreamGenerator.nextDouble: that integer * 0x1.0p-52
+__device__ __forceinline__ double mt_ring_next_double(MtRing &g)
+{
+    return (double)(long long)mt_ring_next52(g) * 0x1.0p-52;
+}
+
+// u >= p for u = nextDouble() without forming u: U * 2^-52 >= p  <=>  U >= ceil(p * 2^52) (both exact).
+__host__ __device__ inline unsigned long long double_threshold52(double p)
+{
+    if (!(p > 0.0)) return 0ull;                      // u >= p always (also for p = -0.0)
+    if (p > 1.0) return ~0ull;                        // never
+    return (unsigned long long)ceil(p * 4503599627370496.0);
 }
 
 // Exact bits % n for 0 <= bits < 2^31 by multiply-high: magic = ceil(2^(31+L) / n), L = ceil(log2 n)
@@ -195,9 +226,9 @@ __host__ __device__ inline FastMod fastmod_make(uint32_t n)
 {
     FastMod f;
     f.n = n;
-    uint32_t L = 0;
-    while ((1u << L) < n) L++;
-    f.shift = 31 + L;
+    uint32_t lg = 0;
+    while ((1u << lg) < n) lg++;
+    f.shift = 31 + lg;
     const uint64_t p = (uint64_t)1 << f.shift;
     f.magic = (uint32_t)((p + n - 1) / n);
     return f;
@@ -211,7 +242,8 @@ __host__ __device__ __forceinline__ uint32_t fastmod(const FastMod &f, uint32_t 
 
 // BitsStreamGenerator.nextInt(n): power-of-two fast path, else the overflow-rejection loop.
 // The caller reserved one word; a rejection (probability < n / 2^31) re-reserves.
-__device__ __forceinline__ int mt_ring_next_int(MtRing &g, const FastMod &f, int lane)
+template <int L>
+__device__ __forceinline__ int mt_ring_next_int(MtRing &g, const FastMod &f, int tl, unsigned mask)
 {
     const int n = (int)f.n;
     if ((n & -n) == n) return (int)(((int64_t)n * (int64_t)(mt_ring_next32(g) >> 1)) >> 31);
@@ -219,22 +251,22 @@ __device__ __forceinline__ int mt_ring_next_int(MtRing &g, const FastMod &f, int
         const int bits = (int)(mt_ring_next32(g) >> 1);
         const int val = (int)fastmod(f, (uint32_t)bits);
         if ((int)((uint32_t)bits - (uint32_t)val + (uint32_t)(n - 1)) >= 0) return val;
-        mt_ring_reserve(g, 1, lane);
+        mt_ring_reserve<L>(g, 1, tl, mask);
     }
 }
 
 // Give the unread ring words back to the cursor so nothing but (par, gen, fed) has to persist.
-__device__ __forceinline__ void mt_ring_close(MtRing &g, int lane)
+__device__ __forceinline__ void mt_ring_close(MtRing &g, int tl, unsigned mask)
 {
-    __syncwarp();
-    if (lane == 0) {
+    __syncwarp(mask);
+    if (tl == 0) {
         MtCursor c = *g.cur;
         if (g.avail <= c.fed) c.fed -= g.avail;
         else { c.par ^= 1; c.fed = MT_N - (g.avail - c.fed); c.gen = MT_N; }   // back into the previous block
         *g.cur = c;
     }
     g.avail = 0;
-    __syncwarp();
+    __syncwarp(mask);
 }
 
 #endif  // __CUDACC__

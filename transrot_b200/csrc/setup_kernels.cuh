@@ -174,20 +174,25 @@ __global__ void init_chains_kernel(InitParams ip)
 
 // Space.calcEnergy on supplied structures: one team per structure, the same device routine
 // the anneal kernel uses for write(n) / writeMovie energies.
-template <int SPL, int W, bool HAS_EXP>
-__global__ void __launch_bounds__(32 * W) total_energy_kernel(DevSystem sys, const double *sites, long long n, double *out, int smem_tables)
+template <int L, int W, int SPL, bool HAS_EXP>
+__global__ void __launch_bounds__(Team<L, W>::TPC) total_energy_kernel(DevSystem sys, const double *sites_g, long long n, double *out, int smem_tables)
 {
+    constexpr int TPC = Team<L, W>::TPC;
     extern __shared__ __align__(16) unsigned char smem[];
+    load_tables(smem, sys);
     const SmemTables tb = carve_tables(smem, sys);
-    load_tables(tb, sys, HAS_EXP);
-    const SmemChain sc = carve_chain(smem + smem_tables, sys, W);
+    ChainSmem *cs = (ChainSmem *)(smem + smem_tables);
+    SiteRec *sites = chain_sites(cs, sys);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned mask = team_mask<L, W>();
     __syncthreads();
+    int info[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
     for (long long i = blockIdx.x; i < n; i += gridDim.x) {
-        SiteRegs<SPL> R;
-        sites_from_global<SPL, W>(R, sites + (size_t)i * sys.n_sites * 3, sys, tid);
-        sites_to_scratch<SPL, W>(R, sc.scratch, sys.pos_site, tid);
-        const double e = team_total_energy<SPL, W, HAS_EXP>(R, sc.scratch, sys, tb.cd, tb.ab, sc.part, warp, lane);
+        sites_from_global<TPC>(sites, sites_g + (size_t)i * sys.n_sites * 3, sys, tid);
+        __syncthreads();
+        const double e = team_total_energy<L, W, SPL, HAS_EXP>(sites, info, sys, tb, cs->part, tid, warp, lane, mask);
         if (tid == 0) out[i] = e;
         __syncthreads();
     }
@@ -195,44 +200,49 @@ __global__ void __launch_bounds__(32 * W) total_energy_kernel(DevSystem sys, con
 
 // eStart / eEnd (Space.java:711-718) for supplied trial coordinates of one particle: the
 // staging + move_energy + reduction path of the anneal kernel.
-template <int SPL, int W, bool HAS_EXP>
-__global__ void __launch_bounds__(32 * W) delta_energy_kernel(DevSystem sys, const double *sites, const int *mol, const double *trial,
-                                                              long long n, double *e_start, double *e_end, double *d_e, int smem_tables)
+template <int L, int W, int SPL, bool HAS_EXP>
+__global__ void __launch_bounds__(Team<L, W>::TPC) delta_energy_kernel(DevSystem sys, const double *sites_g, const int *mol, const double *trial,
+                                                                       long long n, double *e_start, double *e_end, double *d_e, int smem_tables)
 {
+    constexpr int TPC = Team<L, W>::TPC;
     extern __shared__ __align__(16) unsigned char smem[];
+    load_tables(smem, sys);
     const SmemTables tb = carve_tables(smem, sys);
-    load_tables(tb, sys, HAS_EXP);
-    const SmemChain sc = carve_chain(smem + smem_tables, sys, W);
+    ChainSmem *cs = (ChainSmem *)(smem + smem_tables);
+    SiteRec *sites = chain_sites(cs, sys);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int TPC = 32 * W;
-    const int lj_slots = (sys.n_lj_pos + TPC - 1) / TPC;
+    const unsigned mask = team_mask<L, W>();
+    const unsigned char *tab_cd = smem;
+    const unsigned char *tab_ab = smem + (sys.has_exp ? sys.n_types * sys.row_stride : 0);
     __syncthreads();
-    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
-        SiteRegs<SPL> R;
-        sites_from_global<SPL, W>(R, sites + (size_t)i * sys.n_sites * 3, sys, tid);
-        const int m = mol[i];
-        const int sm = tb.mol_off[m + 1] - tb.mol_off[m];
-        const double *tr_i = trial + (size_t)i * TR_MAX_MOL_SITES * 3;
+    int info[SPL];
 #pragma unroll
-        for (int k = 0; k < SPL; k++) {
-            if (info_mol(R.info[k]) == m) {
-                const int a = info_atom(R.info[k]);
-                StageSite st;
-                st.ox = R.x[k]; st.oy = R.y[k]; st.oz = R.z[k];
-                st.nx = tr_i[3 * a]; st.ny = tr_i[3 * a + 1]; st.nz = tr_i[3 * a + 2];
-                st.kq = __dmul_rn(K_VALUE, R.q[k]);
-                st.type = info_type(R.info[k]); st.lj = info_lj(R.info[k]);
-                sc.stage[a] = st;
-            }
+    for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+        sites_from_global<TPC>(sites, sites_g + (size_t)i * sys.n_sites * 3, sys, tid);
+        __syncthreads();
+        const int m = mol[i];
+        const int off = tb.mol_off[m], sm = tb.mol_off[m + 1] - off;
+        const double *tr_i = trial + (size_t)i * TR_MAX_MOL_SITES * 3;
+        if (tid < sm) {
+            const int p = tb.site_pos[off + tid];
+            const SiteRec r = sites[p];
+            const int inf = tb.pos_info[p];
+            StageSite st;
+            st.ox = r.x; st.oy = r.y; st.oz = r.z;
+            st.nx = tr_i[3 * tid]; st.ny = tr_i[3 * tid + 1]; st.nz = tr_i[3 * tid + 2];
+            st.kq = __dmul_rn(K_VALUE, r.q);
+            st.row = info_type(inf) * sys.row_stride; st.lj = info_lj(inf);
+            cs->stage[tid] = st;
         }
         __syncthreads();
         double eS, eE;
-        move_energy<SPL, HAS_EXP>(R, sc.stage, sm, m, tb.cd, tb.ab, sys.n_types, lj_slots, eS, eE);
-        const double dE = team_sum<W>(eE - eS, sc.part, warp, lane);
+        move_energy<TPC, SPL, SPL, HAS_EXP>(sites + tid, info, cs, sm, m, tab_cd, tab_ab, sys.zero_col, eS, eE);
+        const double dE = team_sum<L, W>(eE - eS, cs->part, warp, lane, mask);
         __syncthreads();
-        eS = team_sum<W>(eS, sc.part, warp, lane);
+        eS = team_sum<L, W>(eS, cs->part, warp, lane, mask);
         __syncthreads();
-        eE = team_sum<W>(eE, sc.part, warp, lane);
+        eE = team_sum<L, W>(eE, cs->part, warp, lane, mask);
         if (tid == 0) { e_start[i] = eS; e_end[i] = eE; d_e[i] = dE; }
         __syncthreads();
     }
@@ -240,13 +250,15 @@ __global__ void __launch_bounds__(32 * W) delta_energy_kernel(DevSystem sys, con
 
 // First k outputs of the three streams of each seed, drawn through the ring generator the anneal
 // kernel uses (one warp per seed; `mt` is scratch [n][3][2][624]), in bursts of the sizes a move uses.
-__global__ void __launch_bounds__(128) rng_words_kernel(const long long *seeds, long long n, int k, uint32_t *mt, uint32_t *out)
+template <int L>
+__global__ void __launch_bounds__(4 * L) rng_words_kernel(const long long *seeds, long long n, int k, uint32_t *mt, uint32_t *out)
 {
     __shared__ uint32_t s_ring[4][MT_RING];
     __shared__ MtCursor s_cur[4];
-    const int w = threadIdx.x >> 5;
+    const int w = threadIdx.x / L;
     const long long i = (long long)blockIdx.x * 4 + w;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x % L;
+    const unsigned mask = team_mask<L, 1>();
     if (i >= n) return;
     uint32_t *st = mt + (size_t)i * 3 * 2 * MT_N;
     if (lane == 0) {
@@ -257,29 +269,29 @@ __global__ void __launch_bounds__(128) rng_words_kernel(const long long *seeds, 
         mt_std_seed_long(st + 2 * MT_N, s1);
         mt_std_seed_long(st + 4 * MT_N, s2);
     }
-    __syncwarp();
+    __syncwarp(mask);
     for (int s = 0; s < 3; s++) {
         if (lane == 0) { s_cur[w].par = 0; s_cur[w].gen = MT_N; s_cur[w].fed = MT_N; }
-        __syncwarp();
+        __syncwarp(mask);
         MtRing g;
         mt_ring_open(g, st + s * 2 * MT_N, s_ring[w], &s_cur[w]);
         int j = 0, burst = 1;
         bool resumed = false;
         while (j < k) {
             const int need = (k - j < burst) ? k - j : burst;
-            mt_ring_reserve(g, need, lane);
+            mt_ring_reserve<L>(g, need, lane, mask);
             for (int b = 0; b < need; b++, j++) {
                 const uint32_t v = mt_ring_next32(g);
                 if (lane == 0) out[((size_t)i * 3 + s) * k + j] = v;
             }
             burst = burst % 11 + 1;      // 1..11 words per reservation, like the moves
             if (!resumed && j >= k / 2) {     // suspend / resume, as between two launches
-                mt_ring_close(g, lane);
+                mt_ring_close(g, lane, mask);
                 mt_ring_open(g, st + s * 2 * MT_N, s_ring[w], &s_cur[w]);
                 resumed = true;
             }
         }
-        __syncwarp();
+        __syncwarp(mask);
     }
 }
 

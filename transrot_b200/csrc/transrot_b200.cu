@@ -35,9 +35,12 @@ struct DevBuf {
     }
 };
 
-struct Variant { int W, SPL; };
-// (threads per chain / 32, sites per thread) instantiated below; capacity = 32*W*SPL sites.
-const Variant kVariants[] = { {1, 1}, {1, 2}, {1, 4}, {1, 6}, {4, 2}, {4, 6}, {8, 3}, {8, 6} };
+struct Variant { int L, W, SPL; int tpc() const { return W > 1 ? 32 * W : L; } };
+// (lanes per chain, warps per chain, sites per thread) instantiated below; capacity = tpc * SPL sites.
+// Order = preference of the automatic choice: half-warp teams while the cluster fits 64 sites, then a warp,
+// then a block per chain.
+const Variant kVariants[] = { {16, 1, 1}, {16, 1, 2}, {16, 1, 4}, {32, 1, 2}, {32, 1, 4}, {32, 1, 6},
+                              {32, 4, 6}, {32, 8, 3}, {32, 8, 6} };
 
 }  // namespace
 
@@ -58,10 +61,11 @@ struct tr_ctx {
     DevBuf<int> d_mol_off, d_site_info, d_moveable, d_site_ghost;
     DevBuf<double> d_site_q, d_mol_radius, d_site_def, d_site_mass;
     DevBuf<double2> d_pair_cd, d_pair_ab;
-    DevBuf<int> d_pos_site;
+    DevBuf<int> d_pos_site, d_site_pos, d_pos_info;
+    std::vector<int> h_site_info;
     bool have_propagate_data = false;
     std::vector<int> h_mol_off, h_site_lj;
-    Variant prepared{0, 0};
+    Variant prepared{0, 0, 0};
 
     // schedules
     DevBuf<tr_schedule> d_sched;
@@ -80,7 +84,7 @@ struct tr_ctx {
     DevBuf<tr_point_rec> d_points;
     DevBuf<tr_trace_rec> d_trace;
     int max_points = 0, max_snaps = 0;
-    Variant variant{1, 1};
+    Variant variant{16, 1, 1};
 };
 
 namespace {
@@ -125,124 +129,138 @@ int bind(tr_ctx *ctx)
 bool pick_variant(const tr_ctx *ctx, int n_sites, int tpc, Variant *out)
 {
     for (const Variant &v : kVariants) {
-        if (tpc > 0 && v.W * 32 != tpc) continue;
-        if (tpc == 0 && n_sites <= 192 && v.W != 1) continue;   // auto: warp per chain while it fits
-        if (32 * v.W * v.SPL >= n_sites) { *out = v; return true; }
+        if (tpc > 0 && v.tpc() != tpc) continue;
+        if (v.tpc() * v.SPL >= n_sites) { *out = v; return true; }
     }
     (void)ctx;
     return false;
 }
 
 int chains_per_block(const Variant &v) { return v.W == 1 ? 4 : 1; }
+bool same_variant(const Variant &a, const Variant &b) { return a.L == b.L && a.W == b.W && a.SPL == b.SPL; }
 
 // Site -> (thread, slot) permutation of a kernel variant: sites with Lennard-Jones parameters first, so that
 // the trailing slots are Coulomb-only for every thread (anneal.cuh).
 int prepare_variant(tr_ctx *ctx, const Variant &v)
 {
-    if (ctx->prepared.W == v.W && ctx->prepared.SPL == v.SPL) return TR_OK;
-    const int n_pos = 32 * v.W * v.SPL, S = ctx->sys.n_sites;
-    std::vector<int> pos(n_pos, -1);
+    if (same_variant(ctx->prepared, v)) return TR_OK;
+    const int n_pos = v.tpc() * v.SPL, S = ctx->sys.n_sites, T = ctx->sys.n_types;
+    std::vector<int> pos((size_t)n_pos, -1), inv((size_t)S, 0), pinfo((size_t)n_pos, INFO_UNUSED | (T << 16));
     int p = 0, n_lj = 0;
     for (int i = 0; i < S; i++) if (ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
     n_lj = p;
     for (int i = 0; i < S; i++) if (!ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
+    for (int q = 0; q < S; q++) { inv[(size_t)pos[(size_t)q]] = q; pinfo[(size_t)q] = ctx->h_site_info[(size_t)pos[(size_t)q]]; }
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (int r = upload(ctx, ctx->d_pos_site, pos.data(), pos.size())) return r;
+    if (int r = upload(ctx, ctx->d_site_pos, inv.data(), inv.size())) return r;
+    if (int r = upload(ctx, ctx->d_pos_info, pinfo.data(), pinfo.size())) return r;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->sys.pos_site = ctx->d_pos_site.p;
+    ctx->sys.site_pos = ctx->d_site_pos.p;
+    ctx->sys.pos_info = ctx->d_pos_info.p;
     ctx->sys.n_pos = n_pos;
     ctx->sys.n_lj_pos = n_lj;
     ctx->prepared = v;
     return TR_OK;
 }
 
+int tables_bytes(const tr_ctx *ctx, const Variant &v)
+{
+    return smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp, ctx->sys.n_sites, v.tpc() * v.SPL);
+}
+
+int chain_bytes(const tr_ctx *ctx, const Variant &v) { return smem_chain_bytes(ctx->sys.n_mol, v.tpc() * v.SPL); }
+
 // ---- kernel dispatch -----------------------------------------------------------------------
 
-template <int W, int SPL> struct MinBlocks { static constexpr int value = 1; };
-// blocks per SM the register budget is squeezed for: 7 x 128 threads = 28 chains per SM lets
-// 4096 warp-per-chain chains be resident in one wave on 148 SMs
-template <> struct MinBlocks<1, 1> { static constexpr int value = 7; };
-template <> struct MinBlocks<1, 2> { static constexpr int value = 7; };
-template <> struct MinBlocks<1, 4> { static constexpr int value = 5; };
-template <> struct MinBlocks<1, 6> { static constexpr int value = 4; };
-template <> struct MinBlocks<4, 2> { static constexpr int value = 6; };
-template <> struct MinBlocks<4, 6> { static constexpr int value = 3; };
-template <> struct MinBlocks<8, 3> { static constexpr int value = 2; };
-template <> struct MinBlocks<8, 6> { static constexpr int value = 1; };
+// Blocks per SM the register budget is squeezed for.  Half-warp teams: 7 x 64 threads = 28 chains per SM lets
+// 4096 chains be resident in one wave on 148 SMs with up to 146 registers per thread.
+template <int L, int W, int SPL> struct MinBlocks { static constexpr int value = 1; };
+template <int SPL> struct MinBlocks<16, 1, SPL> { static constexpr int value = 7; };
+template <> struct MinBlocks<32, 1, 2> { static constexpr int value = 4; };
+template <> struct MinBlocks<32, 1, 4> { static constexpr int value = 4; };
+template <> struct MinBlocks<32, 1, 6> { static constexpr int value = 3; };
+template <> struct MinBlocks<32, 4, 6> { static constexpr int value = 3; };
+template <> struct MinBlocks<32, 8, 3> { static constexpr int value = 2; };
 
-template <int SPL, int W, bool HAS_EXP>
-cudaError_t launch_anneal_t(tr_ctx *ctx, const KParams &P)
+template <int L, int W, int SPL, int LJS, bool HAS_EXP>
+cudaError_t launch_anneal_lj(tr_ctx *ctx, const KParams &P)
 {
-    constexpr int CPB = LaunchCfg<W>::CPB;
-    constexpr int MINB = MinBlocks<W, SPL>::value;
+    constexpr int CPB = Team<L, W>::CPB;
+    constexpr int MINB = MinBlocks<L, W, SPL>::value;
     const int smem = P.smem_tables + CPB * P.smem_per_chain;
     const unsigned blocks = (unsigned)((P.n_chains + CPB - 1) / CPB);
     cudaError_t e;
     if (P.trace) {
-        auto kern = anneal_kernel<SPL, W, HAS_EXP, true, 1>;
+        auto kern = anneal_kernel<L, W, SPL, SPL, HAS_EXP, true, 1>;     // tracing: one generic variant
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-        kern<<<blocks, 32 * W * CPB, smem, ctx->stream>>>(P);
+        kern<<<blocks, Team<L, W>::BLOCK, smem, ctx->stream>>>(P);
     } else {
-        auto kern = anneal_kernel<SPL, W, HAS_EXP, false, MINB>;
+        auto kern = anneal_kernel<L, W, SPL, LJS, HAS_EXP, false, MINB>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-        kern<<<blocks, 32 * W * CPB, smem, ctx->stream>>>(P);
+        kern<<<blocks, Team<L, W>::BLOCK, smem, ctx->stream>>>(P);
     }
     return cudaGetLastError();
 }
 
-template <int SPL, int W, bool HAS_EXP>
+// The number of leading slots that can hold Lennard-Jones sites is a compile-time parameter of the kernel
+// (straight-line inner loop); instantiated for 0, about a third, and all slots, rounded up.
+template <int L, int W, int SPL, bool HAS_EXP>
+cudaError_t launch_anneal_t(tr_ctx *ctx, const KParams &P)
+{
+    constexpr int TPC = Team<L, W>::TPC;
+    constexpr int THIRD = (SPL + 2) / 3 < 1 ? 1 : (SPL + 2) / 3;
+    const int lj_slots = (P.sys.n_lj_pos + TPC - 1) / TPC;
+    if (HAS_EXP) return launch_anneal_lj<L, W, SPL, SPL, HAS_EXP>(ctx, P);
+    if (lj_slots == 0) return launch_anneal_lj<L, W, SPL, 0, HAS_EXP>(ctx, P);
+    if (lj_slots <= THIRD) return launch_anneal_lj<L, W, SPL, THIRD, HAS_EXP>(ctx, P);
+    return launch_anneal_lj<L, W, SPL, SPL, HAS_EXP>(ctx, P);
+}
+
+template <int L, int W, int SPL, bool HAS_EXP>
 cudaError_t launch_total_t(tr_ctx *ctx, const double *d_sites, long long n, double *d_out, int smem_tables, int smem_chain)
 {
-    auto kern = total_energy_kernel<SPL, W, HAS_EXP>;
+    auto kern = total_energy_kernel<L, W, SPL, HAS_EXP>;
     const int smem = smem_tables + smem_chain;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
-    kern<<<blocks, 32 * W, smem, ctx->stream>>>(ctx->sys, d_sites, n, d_out, smem_tables);
+    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(ctx->sys, d_sites, n, d_out, smem_tables);
     return cudaGetLastError();
 }
 
-template <int SPL, int W, bool HAS_EXP>
+template <int L, int W, int SPL, bool HAS_EXP>
 cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol, const double *d_trial, long long n,
                            double *d_es, double *d_ee, double *d_de, int smem_tables, int smem_chain)
 {
-    auto kern = delta_energy_kernel<SPL, W, HAS_EXP>;
+    auto kern = delta_energy_kernel<L, W, SPL, HAS_EXP>;
     const int smem = smem_tables + smem_chain;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
-    kern<<<blocks, 32 * W, smem, ctx->stream>>>(ctx->sys, d_sites, d_mol, d_trial, n, d_es, d_ee, d_de, smem_tables);
+    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(ctx->sys, d_sites, d_mol, d_trial, n, d_es, d_ee, d_de, smem_tables);
     return cudaGetLastError();
 }
 
-#define TR_DISPATCH(v, has_exp, CALL)                                                  \
-    do {                                                                               \
-        const int key__ = (v).W * 100 + (v).SPL;                                       \
-        if (has_exp) {                                                                 \
-            switch (key__) {                                                           \
-            case 101: e = CALL(1, 1, true); break;                                     \
-            case 102: e = CALL(2, 1, true); break;                                     \
-            case 104: e = CALL(4, 1, true); break;                                     \
-            case 106: e = CALL(6, 1, true); break;                                     \
-            case 402: e = CALL(2, 4, true); break;                                     \
-            case 406: e = CALL(6, 4, true); break;                                     \
-            case 803: e = CALL(3, 8, true); break;                                     \
-            case 806: e = CALL(6, 8, true); break;                                     \
-            default: e = cudaErrorInvalidValue;                                        \
-            }                                                                          \
-        } else {                                                                       \
-            switch (key__) {                                                           \
-            case 101: e = CALL(1, 1, false); break;                                    \
-            case 102: e = CALL(2, 1, false); break;                                    \
-            case 104: e = CALL(4, 1, false); break;                                    \
-            case 106: e = CALL(6, 1, false); break;                                    \
-            case 402: e = CALL(2, 4, false); break;                                    \
-            case 406: e = CALL(6, 4, false); break;                                    \
-            case 803: e = CALL(3, 8, false); break;                                    \
-            case 806: e = CALL(6, 8, false); break;                                    \
-            default: e = cudaErrorInvalidValue;                                        \
-            }                                                                          \
-        }                                                                              \
+#define TR_DISPATCH_CASES(CALL, HE)                                   \
+    switch (key__) {                                                  \
+    case 160101: e = CALL(16, 1, 1, HE); break;                       \
+    case 160102: e = CALL(16, 1, 2, HE); break;                       \
+    case 160104: e = CALL(16, 1, 4, HE); break;                       \
+    case 320102: e = CALL(32, 1, 2, HE); break;                       \
+    case 320104: e = CALL(32, 1, 4, HE); break;                       \
+    case 320106: e = CALL(32, 1, 6, HE); break;                       \
+    case 320406: e = CALL(32, 4, 6, HE); break;                       \
+    case 320803: e = CALL(32, 8, 3, HE); break;                       \
+    case 320806: e = CALL(32, 8, 6, HE); break;                       \
+    default: e = cudaErrorInvalidValue;                               \
+    }
+
+#define TR_DISPATCH(v, has_exp, CALL)                                          \
+    do {                                                                       \
+        const int key__ = (v).L * 10000 + (v).W * 100 + (v).SPL;               \
+        if (has_exp) { TR_DISPATCH_CASES(CALL, true) } else { TR_DISPATCH_CASES(CALL, false) } \
     } while (0)
 
 int need_chains(tr_ctx *ctx)
@@ -262,8 +280,7 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
                     ctx->threads_per_chain, TR_MAX_SITES);
     ctx->variant = v;
     if (int r = prepare_variant(ctx, v)) return r;
-    const int smem = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp) +
-                     chains_per_block(v) * smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
+    const int smem = tables_bytes(ctx, v) + chains_per_block(v) * chain_bytes(ctx, v);
     if (smem > ctx->max_smem_optin)
         return fail(ctx, TR_ELIMIT, "Error: system needs %d bytes of shared memory per block, device offers %d", smem,
                     ctx->max_smem_optin);
@@ -445,8 +462,9 @@ extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_system = false;
     ctx->n_chains = 0;
-    ctx->prepared = Variant{0, 0};
+    ctx->prepared = Variant{0, 0, 0};
     ctx->h_mol_off.assign(s->mol_site_off, s->mol_site_off + s->n_mol + 1);
+    ctx->h_site_info = info;
     if (int r = upload(ctx, ctx->d_mol_off, s->mol_site_off, (size_t)s->n_mol + 1)) return r;
     if (int r = upload(ctx, ctx->d_site_info, info.data(), info.size())) return r;
     if (int r = upload(ctx, ctx->d_site_q, s->site_q, (size_t)s->n_sites)) return r;
@@ -464,7 +482,8 @@ extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
     DevSystem &d = ctx->sys;
     d.n_mol = s->n_mol; d.n_sites = s->n_sites; d.n_types = s->n_types; d.n_moveable = s->n_moveable;
     d.has_exp = has_exp; d.pad_ = 0;
-    d.n_pos = 0; d.n_lj_pos = 0; d.pos_site = nullptr; d.type_lj = nullptr;
+    d.n_pos = 0; d.n_lj_pos = 0; d.pos_site = nullptr; d.site_pos = nullptr; d.pos_info = nullptr;
+    d.row_stride = (s->n_types + 1) * 16; d.zero_col = s->n_types * 16;
     d.pick_mod = fastmod_make((uint32_t)s->n_moveable);
     d.mol_off = ctx->d_mol_off.p; d.site_info = ctx->d_site_info.p; d.site_q = ctx->d_site_q.p;
     d.pair_cd = ctx->d_pair_cd.p; d.pair_ab = ctx->d_pair_ab.p; d.moveable = ctx->d_moveable.p;
@@ -497,8 +516,9 @@ extern "C" int tr_set_options(tr_ctx *ctx, int64_t trace_moves, int32_t record_p
 {
     if (!ctx) return TR_EINVAL;
     NEED(ctx, trace_moves >= 0, "Error: trace_moves must not be negative");
-    NEED(ctx, threads_per_chain == 0 || threads_per_chain == 32 || threads_per_chain == 128 || threads_per_chain == 256,
-         "Error: threads_per_chain must be 0 (auto), 32, 128 or 256");
+    NEED(ctx, threads_per_chain == 0 || threads_per_chain == 16 || threads_per_chain == 32 || threads_per_chain == 128 ||
+                  threads_per_chain == 256,
+         "Error: threads_per_chain must be 0 (auto), 16, 32, 128 or 256");
     ctx->trace_moves = trace_moves;
     ctx->record_points = record_points ? 1 : 0;
     ctx->record_snapshots = record_snapshots ? 1 : 0;
@@ -608,11 +628,11 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     P.trace_moves = ctx->trace_moves;
     P.max_points = ctx->max_points;
     P.max_snaps = ctx->max_snaps;
-    P.smem_tables = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp);
-    P.smem_per_chain = smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
+    P.smem_tables = tables_bytes(ctx, v);
+    P.smem_per_chain = chain_bytes(ctx, v);
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e;
-#define CALL_ANNEAL(SPL, W, HE) launch_anneal_t<SPL, W, HE>(ctx, P)
+#define CALL_ANNEAL(L, W, SPL, HE) launch_anneal_t<L, W, SPL, HE>(ctx, P)
     TR_DISPATCH(v, ctx->sys.has_exp, CALL_ANNEAL);
 #undef CALL_ANNEAL
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: anneal kernel launch failed: %s", cudaGetErrorString(e));
@@ -800,7 +820,7 @@ extern "C" int tr_total_energy(tr_ctx *ctx, const double *sites, int64_t n, doub
     NEED(ctx, sites && energy && n > 0, "Error: tr_total_energy: bad arguments");
     Variant v;
     if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v)) return fail(ctx, TR_ELIMIT, "Error: system too large");
-    NEED(ctx, ctx->n_chains == 0 || (v.W == ctx->variant.W && v.SPL == ctx->variant.SPL),
+    NEED(ctx, ctx->n_chains == 0 || same_variant(v, ctx->variant),
          "Error: threads_per_chain changed while chains are live; re-initialise the chains first");
     if (int r = prepare_variant(ctx, v)) return r;
     DevBuf<double> d_sites, d_out;
@@ -808,10 +828,10 @@ extern "C" int tr_total_energy(tr_ctx *ctx, const double *sites, int64_t n, doub
     CK(ctx, d_sites.alloc((size_t)n * S3));
     CK(ctx, d_out.alloc((size_t)n));
     CK(ctx, cudaMemcpyAsync(d_sites.p, sites, (size_t)n * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const int st = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp);
-    const int sc = smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
+    const int st = tables_bytes(ctx, v);
+    const int sc = chain_bytes(ctx, v);
     cudaError_t e;
-#define CALL_TOTAL(SPL, W, HE) launch_total_t<SPL, W, HE>(ctx, d_sites.p, n, d_out.p, st, sc)
+#define CALL_TOTAL(L, W, SPL, HE) launch_total_t<L, W, SPL, HE>(ctx, d_sites.p, n, d_out.p, st, sc)
     TR_DISPATCH(v, ctx->sys.has_exp, CALL_TOTAL);
 #undef CALL_TOTAL
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: total-energy kernel launch failed: %s", cudaGetErrorString(e));
@@ -831,7 +851,7 @@ extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *
     for (int64_t i = 0; i < n; i++) NEED(ctx, mol[i] >= 0 && mol[i] < ctx->sys.n_mol, "Error: mol[%lld] out of range", (long long)i);
     Variant v;
     if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v)) return fail(ctx, TR_ELIMIT, "Error: system too large");
-    NEED(ctx, ctx->n_chains == 0 || (v.W == ctx->variant.W && v.SPL == ctx->variant.SPL),
+    NEED(ctx, ctx->n_chains == 0 || same_variant(v, ctx->variant),
          "Error: threads_per_chain changed while chains are live; re-initialise the chains first");
     if (int r = prepare_variant(ctx, v)) return r;
     DevBuf<double> d_sites, d_trial, d_es, d_ee, d_de;
@@ -846,10 +866,10 @@ extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *
     CK(ctx, cudaMemcpyAsync(d_sites.p, sites, (size_t)n * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d_trial.p, trial, (size_t)n * T3 * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d_mol.p, mol, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    const int st = smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp);
-    const int sc = smem_chain_bytes(ctx->sys.n_mol, ctx->sys.n_sites, v.W);
+    const int st = tables_bytes(ctx, v);
+    const int sc = chain_bytes(ctx, v);
     cudaError_t e;
-#define CALL_DELTA(SPL, W, HE) launch_delta_t<SPL, W, HE>(ctx, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, d_de.p, st, sc)
+#define CALL_DELTA(L, W, SPL, HE) launch_delta_t<L, W, SPL, HE>(ctx, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, d_de.p, st, sc)
     TR_DISPATCH(v, ctx->sys.has_exp, CALL_DELTA);
 #undef CALL_DELTA
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: delta-energy kernel launch failed: %s", cudaGetErrorString(e));
@@ -872,7 +892,8 @@ extern "C" int tr_rng_words(tr_ctx *ctx, const int64_t *seeds, int64_t n, int32_
     CK(ctx, d_mt.alloc((size_t)n * 3 * 2 * MT_N));
     CK(ctx, d_out.alloc((size_t)n * 3 * (size_t)k));
     CK(ctx, cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rng_words_kernel<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(d_seeds.p, n, k, d_mt.p, d_out.p);
+    if (ctx->threads_per_chain == 16) rng_words_kernel<16><<<(unsigned)((n + 3) / 4), 64, 0, ctx->stream>>>(d_seeds.p, n, k, d_mt.p, d_out.p);
+    else rng_words_kernel<32><<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(d_seeds.p, n, k, d_mt.p, d_out.p);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpyAsync(out, d_out.p, (size_t)n * 3 * (size_t)k * 4, cudaMemcpyDeviceToHost, ctx->stream));
