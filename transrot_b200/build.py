@@ -30,6 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     ] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    cmd[1:1] = os.environ.get("TR_NVCC_FLAGS", "").split()
     subprocess.check_call(cmd)
     return LIB
 

@@ -55,6 +55,8 @@ struct MoveDesc {        // W > 1 only: what warp 0 decided, broadcast through s
 struct __align__(16) ChainSmem {
     StageSite stage[TR_MAX_MOL_SITES];
     ChainCtrl ctrl;
+    tr_schedule sch;                         // this chain's parameter set
+    uint32_t *mt;                            // global: [3][2][624] ping-pong blocks of this chain
     uint32_t ring[3][MT_RING];
     double part[8];
     MoveDesc desc;
@@ -155,150 +157,205 @@ __device__ __forceinline__ bool team_any(bool p, unsigned mask)
 }
 
 // ---- shared-memory layout ----------------------------------------------------------------------
-// block: [cd (T x (T+1) double2, last column zero)] [ab (same, only with a Born-Mayer term)]
-//        [mol_off (N+1 int)] [moveable (n_moveable int)] [site_pos (S int)] [pos_info (n_pos int)]
-// then CPB x { ChainSmem, com (N x 3 double), sites (n_pos SiteRec) }
+// Everything sits at a COMPILE-TIME offset from the start of dynamic shared memory, so no base
+// pointers have to live in registers (or be recomputed from kernel parameters):
+//   CPB x { ChainSmem, com[NPOS x 3], sites[NPOS] }       chain c at c * CHAIN_BYTES
+//   mol_off[NPOS + 1]  moveable[NPOS]  site_pos[NPOS]  pos_info[NPOS]      (int)
+//   cd[T x (T+1)] double2, last column zero; then ab[...] when a Born-Mayer term exists (runtime size)
 
-__host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
+__host__ __device__ constexpr int align16(int v) { return (v + 15) & ~15; }
 
-__host__ __device__ inline int smem_tables_bytes(int n_mol, int n_moveable, int n_types, bool has_exp, int n_sites, int n_pos)
-{
-    const int tab = n_types * (n_types + 1) * 16;
-    return tab * (has_exp ? 2 : 1) + align16((n_mol + 1) * 4) + align16(n_moveable * 4) + align16(n_sites * 4) + align16(n_pos * 4);
-}
+template <int L, int W, int SPL>
+struct Layout {
+    static constexpr int TPC = Team<L, W>::TPC;
+    static constexpr int CPB = Team<L, W>::CPB;
+    static constexpr int NPOS = TPC * SPL;
+    static constexpr int OFF_COM = align16((int)sizeof(ChainSmem));
+    static constexpr int OFF_SITES = OFF_COM + align16(NPOS * 24);
+    static constexpr int CHAIN_BYTES = OFF_SITES + NPOS * (int)sizeof(SiteRec);
+    static constexpr int OFF_MOL_OFF = CPB * CHAIN_BYTES;
+    static constexpr int OFF_MOVEABLE = OFF_MOL_OFF + align16((NPOS + 1) * 4);
+    static constexpr int OFF_SITE_POS = OFF_MOVEABLE + align16(NPOS * 4);
+    static constexpr int OFF_POS_INFO = OFF_SITE_POS + align16(NPOS * 4);
+    static constexpr int OFF_CD = OFF_POS_INFO + align16(NPOS * 4);
 
-__host__ __device__ inline int smem_chain_bytes(int n_mol, int n_pos)
-{
-    return (int)sizeof(ChainSmem) + align16(n_mol * 24) + n_pos * (int)sizeof(SiteRec);
-}
+    __host__ __device__ static int total_bytes(int n_types, bool has_exp) { return OFF_CD + n_types * (n_types + 1) * 16 * (has_exp ? 2 : 1); }
 
-struct SmemTables {
-    const unsigned char *cd;     // byte-addressed: row offset + column offset
-    const unsigned char *ab;
-    const int *mol_off;
-    const int *moveable;
-    const int *site_pos;
-    const int *pos_info;
-};
-
-__device__ __forceinline__ SmemTables carve_tables(unsigned char *base, const DevSystem &sys)
-{
-    SmemTables t;
-    const int tab = sys.n_types * sys.row_stride;
-    t.cd = base;
-    t.ab = base + (sys.has_exp ? tab : 0);
-    unsigned char *p = base + tab * (sys.has_exp ? 2 : 1);
-    t.mol_off = (const int *)p;  p += align16((sys.n_mol + 1) * 4);
-    t.moveable = (const int *)p; p += align16(sys.n_moveable * 4);
-    t.site_pos = (const int *)p; p += align16(sys.n_sites * 4);
-    t.pos_info = (const int *)p;
-    return t;
-}
-
-__device__ __forceinline__ void load_tables(unsigned char *base, const DevSystem &sys)
-{
-    const int T = sys.n_types, tab = T * (T + 1) * 16;
-    double2 *cd = (double2 *)base, *ab = (double2 *)(base + tab);
-    for (int i = threadIdx.x; i < T * (T + 1); i += blockDim.x) {
-        const int r = i / (T + 1), c = i % (T + 1);
-        cd[i] = (c < T) ? sys.pair_cd[r * T + c] : make_double2(0.0, 0.0);
-        if (sys.has_exp) ab[i] = (c < T) ? sys.pair_ab[r * T + c] : make_double2(0.0, 0.0);
+    __device__ static __forceinline__ ChainSmem *chain(unsigned char *smem, int team) { return (ChainSmem *)(smem + team * CHAIN_BYTES); }
+    __device__ static __forceinline__ double *com(ChainSmem *cs) { return (double *)((unsigned char *)cs + OFF_COM); }
+    __device__ static __forceinline__ SiteRec *sites(ChainSmem *cs) { return (SiteRec *)((unsigned char *)cs + OFF_SITES); }
+    __device__ static __forceinline__ int mol_off(const unsigned char *smem, int m) { return *(const int *)(smem + OFF_MOL_OFF + 4 * m); }
+    __device__ static __forceinline__ int moveable(const unsigned char *smem, int i) { return *(const int *)(smem + OFF_MOVEABLE + 4 * i); }
+    __device__ static __forceinline__ int site_pos(const unsigned char *smem, int i) { return *(const int *)(smem + OFF_SITE_POS + 4 * i); }
+    __device__ static __forceinline__ int pos_info(const unsigned char *smem, int p) { return *(const int *)(smem + OFF_POS_INFO + 4 * p); }
+    __device__ static __forceinline__ const unsigned char *cd(const unsigned char *smem) { return smem + OFF_CD; }
+    __device__ static __forceinline__ const unsigned char *ab(const unsigned char *smem, const DevSystem &sys)
+    {
+        return smem + OFF_CD + (sys.has_exp ? sys.n_types * sys.row_stride : 0);
     }
-    unsigned char *p = base + tab * (sys.has_exp ? 2 : 1);
-    int *mol_off = (int *)p;  p += align16((sys.n_mol + 1) * 4);
-    int *moveable = (int *)p; p += align16(sys.n_moveable * 4);
-    int *site_pos = (int *)p; p += align16(sys.n_sites * 4);
-    int *pos_info = (int *)p;
-    for (int i = threadIdx.x; i <= sys.n_mol; i += blockDim.x) mol_off[i] = sys.mol_off[i];
-    for (int i = threadIdx.x; i < sys.n_moveable; i += blockDim.x) moveable[i] = sys.moveable[i];
-    for (int i = threadIdx.x; i < sys.n_sites; i += blockDim.x) site_pos[i] = sys.site_pos[i];
-    for (int i = threadIdx.x; i < sys.n_pos; i += blockDim.x) pos_info[i] = sys.pos_info[i];
-}
 
-__device__ __forceinline__ double *chain_com(ChainSmem *cs) { return (double *)(cs + 1); }
-__device__ __forceinline__ SiteRec *chain_sites(ChainSmem *cs, const DevSystem &sys)
-{
-    return (SiteRec *)((unsigned char *)(cs + 1) + align16(sys.n_mol * 24));
-}
+    __device__ static __forceinline__ void load_tables(unsigned char *smem, const DevSystem &sys)
+    {
+        const int T = sys.n_types, tab = T * (T + 1) * 16;
+        double2 *cdp = (double2 *)(smem + OFF_CD), *abp = (double2 *)(smem + OFF_CD + tab);
+        for (int i = threadIdx.x; i < T * (T + 1); i += blockDim.x) {
+            const int r = i / (T + 1), c = i % (T + 1);
+            cdp[i] = (c < T) ? sys.pair_cd[r * T + c] : make_double2(0.0, 0.0);
+            if (sys.has_exp) abp[i] = (c < T) ? sys.pair_ab[r * T + c] : make_double2(0.0, 0.0);
+        }
+        int *mo = (int *)(smem + OFF_MOL_OFF), *mv = (int *)(smem + OFF_MOVEABLE);
+        int *sp = (int *)(smem + OFF_SITE_POS), *pi = (int *)(smem + OFF_POS_INFO);
+        for (int i = threadIdx.x; i <= sys.n_mol; i += blockDim.x) mo[i] = sys.mol_off[i];
+        for (int i = threadIdx.x; i < sys.n_moveable; i += blockDim.x) mv[i] = sys.moveable[i];
+        for (int i = threadIdx.x; i < sys.n_sites; i += blockDim.x) sp[i] = sys.site_pos[i];
+        for (int i = threadIdx.x; i < NPOS; i += blockDim.x) pi[i] = sys.pos_info[i];
+    }
+};
 
 // ---- energies ----------------------------------------------------------------------------------
 
-// One staged site against all SPL positions of this thread: straight-line code, 2*SPL independent
-// pair evaluations for the scheduler to interleave.  LJN = how many leading slots take the
-// Lennard-Jones form (compile time); the rest are Coulomb-only.
-template <int SPL, int LJN, int MODE_LJ>
-__device__ __forceinline__ void stage_site_energy(const StageSite &st, const unsigned char *tab_cd, const unsigned char *tab_ab,
-                                                  const double (&x)[SPL], const double (&y)[SPL], const double (&z)[SPL],
-                                                  const double (&qm)[SPL], const double (&off)[SPL], const int (&col)[SPL],
-                                                  double &eS, double &eE)
+// NS consecutive slots of this thread against one staged site: 2*NS pair evaluations (old and trial
+// position) written operation by operation across the group, so that each dependent FP64 chain has
+// 2*NS - 1 independent instructions between its links (FP64 issues every 2 cycles per warp and a
+// dependent result is ready after ~8: a group of four saturates the pipe from a single warp).
+template <int NS, int MODE>
+__device__ __forceinline__ void group_energy(const StageSite &st, const unsigned char *tab_cd, const unsigned char *tab_ab,
+                                             const double *x, const double *y, const double *z, const double *qm, const int *col,
+                                             double &eS, double &eE)
 {
-    double s[SPL], e[SPL];
+    constexpr int G = 2 * NS;
+    double kqq[NS], r2[G], y0[G], t[G], e[G], p[G], ri[G];
+    double2 cd[NS], ab[NS];
 #pragma unroll
-    for (int k = 0; k < SPL; k++) {
-        const double kqq = st.kq * qm[k];                // kTimesQ * atom.q
-        const double ox = x[k] - st.ox, oy = y[k] - st.oy, oz = z[k] - st.oz;
-        const double nx = x[k] - st.nx, ny = y[k] - st.ny, nz = z[k] - st.nz;
-        const double2 z2 = make_double2(0.0, 0.0);
-        if (k < LJN) {
-            const double2 cd = *(const double2 *)(tab_cd + st.row + col[k]);
-            double2 ab = z2;
-            if (MODE_LJ == 2) ab = *(const double2 *)(tab_ab + st.row + col[k]);
-            s[k] = pair_accumulate<MODE_LJ>(0.0, ox, oy, oz, off[k], kqq, cd, ab);
-            e[k] = pair_accumulate<MODE_LJ>(0.0, nx, ny, nz, off[k], kqq, cd, ab);
-        } else {
-            s[k] = pair_accumulate<0>(0.0, ox, oy, oz, off[k], kqq, z2, z2);
-            e[k] = pair_accumulate<0>(0.0, nx, ny, nz, off[k], kqq, z2, z2);
+    for (int s = 0; s < NS; s++) {
+        kqq[s] = st.kq * qm[s];                              // kTimesQ * atom.q
+        if (MODE >= 1) cd[s] = *(const double2 *)(tab_cd + st.row + col[s]);
+        if (MODE >= 2) ab[s] = *(const double2 *)(tab_ab + st.row + col[s]);
+    }
+    {
+        double dx[G], dy[G], dz[G];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            dx[2 * s] = x[s] - st.ox; dx[2 * s + 1] = x[s] - st.nx;
+            dy[2 * s] = y[s] - st.oy; dy[2 * s + 1] = y[s] - st.ny;
+            dz[2 * s] = z[s] - st.oz; dz[2 * s + 1] = z[s] - st.nz;
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) r2[g] = dx[g] * dx[g];
+#pragma unroll
+        for (int g = 0; g < G; g++) r2[g] = fma(dy[g], dy[g], r2[g]);
+#pragma unroll
+        for (int g = 0; g < G; g++) r2[g] = fma(dz[g], dz[g], r2[g]);
+    }
+    // 1/r: MUFU.RSQ64H seed (~22 bits) + one cubic Newton step, y (1 + e/2 + 3e^2/8), e = 1 - r2 y^2
+#pragma unroll
+    for (int g = 0; g < G; g++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[g]) : "d"(r2[g]));
+#pragma unroll
+    for (int g = 0; g < G; g++) t[g] = r2[g] * y0[g];
+#pragma unroll
+    for (int g = 0; g < G; g++) e[g] = fma(-t[g], y0[g], 1.0);
+#pragma unroll
+    for (int g = 0; g < G; g++) p[g] = fma(e[g], 0.375, 0.5);
+#pragma unroll
+    for (int g = 0; g < G; g++) e[g] = y0[g] * e[g];
+#pragma unroll
+    for (int g = 0; g < G; g++) ri[g] = fma(p[g], e[g], y0[g]);
+    if (MODE >= 1) {
+        double r6[G], lj[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) t[g] = ri[g] * ri[g];
+#pragma unroll
+        for (int g = 0; g < G; g++) r6[g] = t[g] * t[g];
+#pragma unroll
+        for (int g = 0; g < G; g++) r6[g] = r6[g] * t[g];
+#pragma unroll
+        for (int g = 0; g < G; g++) lj[g] = fma(cd[g / 2].y, r6[g], -cd[g / 2].x);      // D/r^6 - C
+#pragma unroll
+        for (int s = 0; s < NS; s++) { eS = fma(lj[2 * s], r6[2 * s], eS); eE = fma(lj[2 * s + 1], r6[2 * s + 1], eE); }
+    }
+    if (MODE >= 2) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            eS = fma(ab[s].x, exp(-ab[s].y * (r2[2 * s] * ri[2 * s])), eS);
+            eE = fma(ab[s].x, exp(-ab[s].y * (r2[2 * s + 1] * ri[2 * s + 1])), eE);
         }
     }
 #pragma unroll
-    for (int k = 0; k < SPL; k++) { eS += s[k]; eE += e[k]; }
+    for (int s = 0; s < NS; s++) { eS = fma(kqq[s], ri[2 * s], eS); eE = fma(kqq[s], ri[2 * s + 1], eE); }
+}
+
+// One staged site against all SPL positions of this thread, in groups of two slots.  The first LJN
+// slots take the Lennard-Jones form (MODE_LJ), the rest are Coulomb-only.
+template <int SPL, int LJN, int MODE_LJ>
+__device__ __forceinline__ void stage_site_energy(const StageSite &st, const unsigned char *tab_cd, const unsigned char *tab_ab,
+                                                  const double (&x)[SPL], const double (&y)[SPL], const double (&z)[SPL],
+                                                  const double (&qm)[SPL], const int (&col)[SPL], double &eS, double &eE)
+{
+#pragma unroll
+    for (int k = 0; k < SPL; k += 2) {
+        if (k + 1 < SPL) {
+            if (k + 1 < LJN) group_energy<2, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            else if (k < LJN) {
+                group_energy<1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+                group_energy<1, 0>(st, tab_cd, tab_ab, x + k + 1, y + k + 1, z + k + 1, qm + k + 1, col + k + 1, eS, eE);
+            } else group_energy<2, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+        } else {
+            if (k < LJN) group_energy<1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            else group_energy<1, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+        }
+    }
 }
 
 // Per-thread partial sums of eStart / eEnd (Space.java:711-718) for the particle staged in
 // cs->stage (sm sites, index m).  `mine` = this thread's first position record; slot k is at
 // mine[k * TPC]; info[k] its info word.  LJS = slots that may hold Lennard-Jones sites
-// (compile time, >= the system's actual count).
+// (compile time, >= the system's actual count).  Positions of m itself are taken out by a zero
+// charge, the all-zero table column and a far-away x coordinate (no r = 0, no branch).
 template <int TPC, int SPL, int LJS, bool HAS_EXP>
 __device__ __forceinline__ void move_energy(const SiteRec *mine, const int (&info)[SPL], const ChainSmem *cs, int sm, int m,
                                             const unsigned char *tab_cd, const unsigned char *tab_ab, int zero_col,
                                             double &eS, double &eE)
 {
     eS = 0.0; eE = 0.0;
-    double x[SPL], y[SPL], z[SPL], qm[SPL], off[SPL];
+    double x[SPL], y[SPL], z[SPL], qm[SPL];
     int col[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; k++) {
         const SiteRec r = mine[k * TPC];
         const bool on = info_mol(info[k]) != m;
-        x[k] = r.x; y[k] = r.y; z[k] = r.z;
+        x[k] = on ? r.x : FAR_AWAY; y[k] = r.y; z[k] = r.z;
         qm[k] = on ? r.q : 0.0;
-        off[k] = on ? 0.0 : 1.0;
         col[k] = on ? info_col(info[k]) : zero_col;
     }
     for (int a = 0; a < sm; a++) {
         const StageSite st = cs->stage[a];
-        if (HAS_EXP) stage_site_energy<SPL, SPL, 2>(st, tab_cd, tab_ab, x, y, z, qm, off, col, eS, eE);
-        else if (LJS > 0 && st.lj) stage_site_energy<SPL, LJS, 1>(st, tab_cd, tab_ab, x, y, z, qm, off, col, eS, eE);
-        else stage_site_energy<SPL, 0, 0>(st, tab_cd, tab_ab, x, y, z, qm, off, col, eS, eE);
+        if (HAS_EXP) stage_site_energy<SPL, SPL, 2>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
+        else if (LJS > 0 && st.lj) stage_site_energy<SPL, LJS, 1>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
+        else stage_site_energy<SPL, 0, 0>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
     }
 }
 
 // Space.calcEnergy (Space.java:648-658): sum over particle pairs x < y of Molecule.calcEnergy(x -> y);
 // the site of the lower-indexed particle is `this` (its kTimesQ multiplies the other's q).
 template <int L, int W, int SPL, bool HAS_EXP>
-__device__ __forceinline__ double team_total_energy(const SiteRec *sites, const int (&info)[SPL], const DevSystem &sys,
-                                                    const SmemTables &tb, double *part, int tid, int warp, int lane, unsigned mask)
+__device__ __forceinline__ double team_total_energy(const unsigned char *smem, ChainSmem *cs, const DevSystem &sys,
+                                                    int tid, int warp, int lane, unsigned mask)
 {
-    constexpr int TPC = Team<L, W>::TPC;
+    using Lay = Layout<L, W, SPL>;
+    constexpr int TPC = Lay::TPC;
+    const SiteRec *sites = Lay::sites(cs);
+    const unsigned char *tab_cd = Lay::cd(smem), *tab_ab = Lay::ab(smem, sys);
     double acc = 0.0;
     double x[SPL], y[SPL], z[SPL], q[SPL];
+    int info[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; k++) {
         const SiteRec r = sites[tid + k * TPC];
         x[k] = r.x; y[k] = r.y; z[k] = r.z; q[k] = r.q;
+        info[k] = Lay::pos_info(smem, tid + k * TPC);
     }
-    for (int p = 0; p < sys.n_pos; p++) {
-        const int infi = tb.pos_info[p];
+    for (int p = 0; p < Lay::NPOS; p++) {
+        const int infi = Lay::pos_info(smem, p);
         if (!info_valid(infi)) continue;
         const int mi = info_mol(infi), row = info_type(infi) * sys.row_stride;
         const SiteRec ri = sites[p];
@@ -306,30 +363,30 @@ __device__ __forceinline__ double team_total_energy(const SiteRec *sites, const 
 #pragma unroll
         for (int k = 0; k < SPL; k++) {
             if (info_valid(info[k]) && mi < info_mol(info[k])) {
-                const double2 cd = *(const double2 *)(tb.cd + row + info_col(info[k]));
+                const double2 cd = *(const double2 *)(tab_cd + row + info_col(info[k]));
                 double2 ab = make_double2(0.0, 0.0);
-                if (HAS_EXP) ab = *(const double2 *)(tb.ab + row + info_col(info[k]));
+                if (HAS_EXP) ab = *(const double2 *)(tab_ab + row + info_col(info[k]));
                 acc = pair_accumulate<HAS_EXP ? 2 : 1>(acc, x[k] - ri.x, y[k] - ri.y, z[k] - ri.z, 0.0, kqi * q[k], cd, ab);
             }
         }
     }
-    return team_sum<L, W>(acc, part, warp, lane, mask);
+    return team_sum<L, W>(acc, cs->part, warp, lane, mask);
 }
 
-// global [S][3] (site order) <-> shared SiteRec[n_pos] (position order)
-template <int TPC>
+// global [S][3] (site order) <-> shared SiteRec[NPOS] (position order)
+template <int TPC, int NPOS>
 __device__ __forceinline__ void sites_to_global(const SiteRec *sites, double *dst, const DevSystem &sys, int tid)
 {
-    for (int p = tid; p < sys.n_pos; p += TPC) {
+    for (int p = tid; p < NPOS; p += TPC) {
         const int i = sys.pos_site[p];
         if (i >= 0) { const SiteRec r = sites[p]; dst[3 * i] = r.x; dst[3 * i + 1] = r.y; dst[3 * i + 2] = r.z; }
     }
 }
 
-template <int TPC>
+template <int TPC, int NPOS>
 __device__ __forceinline__ void sites_from_global(SiteRec *sites, const double *src, const DevSystem &sys, int tid)
 {
-    for (int p = tid; p < sys.n_pos; p += TPC) {
+    for (int p = tid; p < NPOS; p += TPC) {
         const int i = sys.pos_site[p];
         SiteRec r;
         if (i >= 0) { r.x = src[3 * i]; r.y = src[3 * i + 1]; r.z = src[3 * i + 2]; r.q = sys.site_q[i]; }
@@ -343,15 +400,12 @@ __device__ __forceinline__ void sites_from_global(SiteRec *sites, const double *
 // write(n) (Space.java:550-623 as far as the device is concerned): calcEnergy, keep the
 // structure, track the minimum (Space.java:614-617).
 template <int L, int W, int SPL, bool HAS_EXP>
-__device__ __noinline__ double snapshot(const KParams &P, long long chain, ChainSmem *cs, const SmemTables tb, int n,
+__device__ __noinline__ double snapshot(const KParams &P, unsigned char *smem, long long chain, int team, int n,
                                         int tid, int warp, int lane, unsigned mask)
 {
-    constexpr int TPC = Team<L, W>::TPC;
-    const SiteRec *sites = chain_sites(cs, P.sys);
-    int info[SPL];
-#pragma unroll
-    for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
-    const double e = team_total_energy<L, W, SPL, HAS_EXP>(sites, info, P.sys, tb, cs->part, tid, warp, lane, mask);
+    using Lay = Layout<L, W, SPL>;
+    ChainSmem *cs = Lay::chain(smem, team);
+    const double e = team_total_energy<L, W, SPL, HAS_EXP>(smem, cs, P.sys, tid, warp, lane, mask);
     ChainCtrl *c = &cs->ctrl;
     const int k = c->n_snaps;
     if (k < P.max_snaps) {
@@ -360,7 +414,8 @@ __device__ __noinline__ double snapshot(const KParams &P, long long chain, Chain
             P.snap_tooth[chain * P.max_snaps + k] = n;
         }
         if (P.snap_sites)
-            sites_to_global<TPC>(sites, P.snap_sites + ((size_t)chain * P.max_snaps + k) * (size_t)P.sys.n_sites * 3, P.sys, tid);
+            sites_to_global<Lay::TPC, Lay::NPOS>(Lay::sites(cs), P.snap_sites + ((size_t)chain * P.max_snaps + k) * (size_t)P.sys.n_sites * 3,
+                                                 P.sys, tid);
     }
     team_sync<L, W>(mask);
     if (tid == 0) {
@@ -381,12 +436,13 @@ __device__ __forceinline__ void refresh_derived(ChainSmem *cs)
 // End of a point (Main.java:225-240) and, when it was the last one, end of the tooth (:242-257).
 // Returns true when the chain has finished.  Rare (once per movePerPt moves): kept out of line.
 template <int L, int W, int SPL, bool HAS_EXP>
-__device__ __noinline__ bool end_of_point(const KParams &P, long long chain, ChainSmem *cs, const SmemTables tb,
+__device__ __noinline__ bool end_of_point(const KParams &P, unsigned char *smem, long long chain, int team,
                                           int tid, int warp, int lane, unsigned mask)
 {
-    constexpr int TPC = Team<L, W>::TPC;
+    using Lay = Layout<L, W, SPL>;
+    ChainSmem *cs = Lay::chain(smem, team);
     ChainCtrl *c = &cs->ctrl;
-    const tr_schedule &sch = P.sched[c->sched];
+    const tr_schedule &sch = cs->sch;
     const int numTeeth = sch.static_temp ? 1 : sch.num_teeth;   // Main.java:74-76
     const double t = c->t;
     {
@@ -399,12 +455,7 @@ __device__ __noinline__ bool end_of_point(const KParams &P, long long chain, Cha
             if (t_next < 0.0) t_next = 0.0;
         }
         double me = __longlong_as_double(0x7ff8000000000000LL);
-        if (movie && P.points) {
-            int info[SPL];
-#pragma unroll
-            for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
-            me = team_total_energy<L, W, SPL, HAS_EXP>(chain_sites(cs, P.sys), info, P.sys, tb, cs->part, tid, warp, lane, mask);
-        }
+        if (movie && P.points) me = team_total_energy<L, W, SPL, HAS_EXP>(smem, cs, P.sys, tid, warp, lane, mask);
         if (tid == 0) {
             if (P.points && pi < P.max_points) {
                 tr_point_rec r;
@@ -444,7 +495,7 @@ __device__ __noinline__ bool end_of_point(const KParams &P, long long chain, Cha
     }
     team_sync<L, W>(mask);
     if (!start_finale) {
-        snapshot<L, W, SPL, HAS_EXP>(P, chain, cs, tb, x + 1, tid, warp, lane, mask);   // write(x+1)
+        snapshot<L, W, SPL, HAS_EXP>(P, smem, chain, team, x + 1, tid, warp, lane, mask);   // write(x+1)
         if (c->x >= numTeeth) {
             if (tid == 0) c->done = 1;
             team_sync<L, W>(mask);
@@ -456,15 +507,22 @@ __device__ __noinline__ bool end_of_point(const KParams &P, long long chain, Cha
 
 // ---- the kernel ------------------------------------------------------------------------------
 
+// Ring refills happen once per ~3 moves and are kept out of the move loop's register budget.
+template <int L>
+__device__ __noinline__ int refill_stream(ChainSmem *cs, int stream, int wr, int tl, unsigned mask)
+{
+    return mt_ring_refill_words<L>(cs->mt + stream * 2 * MT_N, cs->ring[stream], &cs->ctrl.rng[stream], wr, tl, mask);
+}
+
 template <int L, int W, int SPL, int LJS, bool HAS_EXP, bool TRACE, int MINB>
 __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const __grid_constant__ KParams P)
 {
-    constexpr int TPC = Team<L, W>::TPC;
-    constexpr int CPB = Team<L, W>::CPB;
+    using Lay = Layout<L, W, SPL>;
+    constexpr int TPC = Lay::TPC;
+    constexpr int CPB = Lay::CPB;
     extern __shared__ __align__(16) unsigned char smem[];
     const DevSystem &sys = P.sys;
-    load_tables(smem, sys);
-    const SmemTables tb = carve_tables(smem, sys);
+    Lay::load_tables(smem, sys);
 
     const int lane = threadIdx.x & 31;
     const int team = (W == 1) ? (int)threadIdx.x / TPC : 0;
@@ -472,9 +530,9 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
     const int tid = (W == 1) ? (int)threadIdx.x % TPC : (int)threadIdx.x;   // thread index inside the team
     const unsigned mask = team_mask<L, W>();
     const long long chain = (long long)blockIdx.x * CPB + team;
-    ChainSmem *cs = (ChainSmem *)(smem + P.smem_tables + team * P.smem_per_chain);
-    double *com = chain_com(cs);
-    SiteRec *sites = chain_sites(cs, sys);
+    ChainSmem *cs = Lay::chain(smem, team);
+    double *com = Lay::com(cs);
+    SiteRec *sites = Lay::sites(cs);
     const bool active = chain < P.n_chains;
     const long long ch = active ? chain : 0;                 // idle teams shadow chain 0 read-only
 
@@ -486,33 +544,31 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
         for (int i = tid; i < (int)(sizeof(ChainCtrl) / 4); i += TPC) dst[i] = src[i];
         const double *cg = P.com + (size_t)ch * sys.n_mol * 3;
         for (int i = tid; i < sys.n_mol * 3; i += TPC) com[i] = cg[i];
-        sites_from_global<TPC>(sites, P.sites + (size_t)ch * sys.n_sites * 3, sys, tid);
+        sites_from_global<TPC, Lay::NPOS>(sites, P.sites + (size_t)ch * sys.n_sites * 3, sys, tid);
+    }
+    team_sync<L, W>(mask);
+    if (tid == 0) {
+        cs->sch = P.sched[c->sched];
+        cs->mt = P.mt + (size_t)ch * 3 * 2 * MT_N;
+        refresh_derived(cs);
     }
     __syncthreads();
-    if (tid == 0) refresh_derived(cs);
-    team_sync<L, W>(mask);
     if (!active || c->done) return;     // whole teams leave together (W > 1: the whole block)
 
-    const tr_schedule &sch = P.sched[c->sched];   // global (L1-resident, team-uniform): fields are re-read on use
+    const tr_schedule &sch = cs->sch;
     const int S = sys.n_sites;
     const FastMod three = fastmod_make(3);
     const SiteRec *mine = sites + tid;            // this thread's positions: mine[k * TPC]
-    const unsigned char *tab_cd = smem;           // pair tables sit at the start of dynamic shared memory
-    const unsigned char *tab_ab = smem + (sys.has_exp ? sys.n_types * sys.row_stride : 0);
+    const unsigned char *tab_cd = Lay::cd(smem), *tab_ab = Lay::ab(smem, sys);
     int info[SPL];
 #pragma unroll
-    for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
-    MtRing gM, gS, gR;
-    {
-        uint32_t *mt = P.mt + (size_t)chain * 3 * 2 * MT_N;
-        mt_ring_open(gM, mt + STREAM_M * 2 * MT_N, cs->ring[STREAM_M], &c->rng[STREAM_M]);
-        mt_ring_open(gS, mt + STREAM_S * 2 * MT_N, cs->ring[STREAM_S], &c->rng[STREAM_S]);
-        mt_ring_open(gR, mt + STREAM_R * 2 * MT_N, cs->ring[STREAM_R], &c->rng[STREAM_R]);
-    }
+    for (int k = 0; k < SPL; k++) info[k] = Lay::pos_info(smem, tid + k * TPC);
+    // ring cursors: (read slot, unread words) per stream, team-uniform
+    int rdM = 0, avM = 0, rdS = 0, avS = 0, rdR = 0, avR = 0;
 
     // Main.java:64,71: write(0) and startingEnergy = calcEnergy()
     if (!c->started) {
-        const double e0 = snapshot<L, W, SPL, HAS_EXP>(P, chain, cs, tb, 0, tid, warp, lane, mask);
+        const double e0 = snapshot<L, W, SPL, HAS_EXP>(P, smem, chain, team, 0, tid, warp, lane, mask);
         if (tid == 0) {
             c->start_energy = e0;
             c->running = e0;
@@ -523,6 +579,10 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
     }
 
     long long budget = P.max_moves > 0 ? P.max_moves : 0x7fffffffffffffffLL;
+
+// one tempered word / the 52-bit integer of nextDouble / nextDouble itself from stream X (M, S or R)
+#define RING_NEXT32(X) (av##X--, rd##X = (rd##X + 1) & (MT_RING - 1), cs->ring[STREAM_##X][(rd##X - 1) & (MT_RING - 1)])
+#define RING_RESERVE(X, need) while (av##X < (need)) av##X += refill_stream<L>(cs, STREAM_##X, rd##X + av##X, tid, mask)
 
     while (budget > 0) {
         // ---------------------------------------------------------------- z-loop (Main.java:195)
@@ -542,30 +602,52 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
             int m = 0, rot = 0, axis = -1, magwalk = 0;
             double va = 0.0, vb = 0.0, vc = 0.0;       // translation vector or (sin, cos)
             if (warp == 0) {
-                mt_ring_reserve<L>(gS, 9, tid, mask);  // pick + 3 doubles + Metropolis double
-                mt_ring_reserve<L>(gM, 4, tid, mask);  // two doubles, always (Main.java:199-208)
-                mt_ring_reserve<L>(gR, 3, tid, mask);  // angle double + axis
-                const int pick = mt_ring_next_int<L>(gS, sys.pick_mod, tid, mask);   // Space.java:736
-                m = tb.moveable[pick];
-                const int sm0 = tb.mol_off[m + 1] - tb.mol_off[m];
-                // r.nextDouble() >= 0.5 (Main.java:199): the top bit of the first word; both words are consumed
-                const unsigned long long u1 = mt_ring_next52(gM);
-                const unsigned long long u2 = mt_ring_next52(gM);                    // :200 or :208
-                rot = (u1 >= (1ull << 51) && sm0 > 1) ? 1 : 0;
+                RING_RESERVE(S, 9);                    // pick + 3 doubles + Metropolis double
+                RING_RESERVE(M, 4);                    // two doubles, always (Main.java:199-208)
+                RING_RESERVE(R, 3);                    // angle double + axis
+                int pick;                              // Space.java:736: r.nextInt(moveableMolecules.size())
+                {
+                    const int n = (int)sys.pick_mod.n;
+                    if ((n & -n) == n) pick = (int)(((long long)n * (long long)(RING_NEXT32(S) >> 1)) >> 31);
+                    else for (;;) {
+                        const int bits = (int)(RING_NEXT32(S) >> 1);
+                        pick = (int)fastmod(sys.pick_mod, (uint32_t)bits);
+                        if ((int)((uint32_t)bits - (uint32_t)pick + (uint32_t)(n - 1)) >= 0) break;
+                        RING_RESERVE(S, 9);
+                    }
+                }
+                m = Lay::moveable(smem, pick);
+                const int sm0 = Lay::mol_off(smem, m + 1) - Lay::mol_off(smem, m);
+                // r.nextDouble() >= 0.5 (Main.java:199) is the top bit of the first word; both words are consumed.
+                // The second double (:200 or :208) is compared as a 52-bit integer against ceil(prob * 2^52).
+                const uint32_t w0 = RING_NEXT32(M);
+                (void)RING_NEXT32(M);
+                const uint32_t h2 = RING_NEXT32(M) >> 6, l2 = RING_NEXT32(M) >> 6;
+                const unsigned long long u2 = ((unsigned long long)h2 << 26) | l2;
+                rot = ((w0 >> 31) && sm0 > 1) ? 1 : 0;
                 if (rot) {
                     magwalk = (u2 >= cs->thr_rot) ? 0 : 1;
                     const double maxR = magwalk ? JAVA_TWO_PI : c->maxRot;
-                    const double u = mt_ring_next_double(gR);                        // Molecule.java:67
+                    const uint32_t hr = RING_NEXT32(R) >> 6, lr = RING_NEXT32(R) >> 6;               // Molecule.java:67
+                    const double u = (double)(long long)(((unsigned long long)hr << 26) | lr) * 0x1.0p-52;
                     const double rotAmount = __dmul_rn(__dmul_rn(__dsub_rn(u, 0.5), 2.0), maxR);
-                    axis = mt_ring_next_int<L>(gR, three, tid, mask);                // Molecule.java:68
+                    for (;;) {                                                                    // Molecule.java:68: nextInt(3)
+                        const int bits = (int)(RING_NEXT32(R) >> 1);
+                        axis = (int)fastmod(three, (uint32_t)bits);
+                        if ((int)((uint32_t)bits - (uint32_t)axis + 2u) >= 0) break;
+                        RING_RESERVE(R, 1);
+                    }
                     sincos(rotAmount, &va, &vb);
                 } else {
                     magwalk = (u2 >= cs->thr_trans) ? 0 : 1;
                     const double maxD = c->maxD;
                     const double maxT = magwalk ? __dmul_rn(maxD, sch.magwalk_factor_trans) : maxD;
-                    const double ux = mt_ring_next_double(gS);                       // Space.java:694-696
-                    const double uy = mt_ring_next_double(gS);
-                    const double uz = mt_ring_next_double(gS);
+                    const uint32_t hx = RING_NEXT32(S) >> 6, lx = RING_NEXT32(S) >> 6;               // Space.java:694-696
+                    const uint32_t hy = RING_NEXT32(S) >> 6, ly = RING_NEXT32(S) >> 6;
+                    const uint32_t hz = RING_NEXT32(S) >> 6, lz = RING_NEXT32(S) >> 6;
+                    const double ux = (double)(long long)(((unsigned long long)hx << 26) | lx) * 0x1.0p-52;
+                    const double uy = (double)(long long)(((unsigned long long)hy << 26) | ly) * 0x1.0p-52;
+                    const double uz = (double)(long long)(((unsigned long long)hz << 26) | lz) * 0x1.0p-52;
                     va = __dsub_rn(__dmul_rn(__dmul_rn(ux, 2.0), maxT), maxT);
                     vb = __dsub_rn(__dmul_rn(__dmul_rn(uy, 2.0), maxT), maxT);
                     vc = __dsub_rn(__dmul_rn(__dmul_rn(uz, 2.0), maxT), maxT);
@@ -580,16 +662,16 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
                 const MoveDesc d = cs->desc;
                 va = d.a; vb = d.b; vc = d.c; m = d.m; rot = d.rot; axis = d.axis; magwalk = d.magwalk;
             }
-            const int off = tb.mol_off[m];
-            const int sm = tb.mol_off[m + 1] - off;
+            const int off = Lay::mol_off(smem, m);
+            const int sm = Lay::mol_off(smem, m + 1) - off;
 
             // -- trial geometry: thread a < sm handles site a of m; stage old + trial coordinates
             bool oob = false;
             int my_pos = 0;
             if (tid < sm) {
-                my_pos = tb.site_pos[off + tid];
+                my_pos = Lay::site_pos(smem, off + tid);
                 const SiteRec r = sites[my_pos];
-                const int inf = tb.pos_info[my_pos];
+                const int inf = Lay::pos_info(smem, my_pos);
                 double ox = r.x, oy = r.y, oz = r.z, tx, ty, tz;
                 if (rot) {
                     // Molecule.java:70-95, operation for operation, no contraction (va = sin, vb = cos)
@@ -645,7 +727,8 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
                 acc = 1;
                 if (dE > 0.0) {
                     if (warp == 0) {
-                        rnd = mt_ring_next_double(gS);                           // drawn before the T == 0 test
+                        const uint32_t hm = RING_NEXT32(S) >> 6, lm = RING_NEXT32(S) >> 6;           // drawn before the T == 0 test
+                        rnd = (double)(long long)(((unsigned long long)hm << 26) | lm) * 0x1.0p-52;
                         if (t == 0.0) acc = 0;
                         else {
                             const double test = exp(__ddiv_rn(__dmul_rn(-1.0, dE), __dmul_rn(BOLTZMANN_CONSTANT, t)));
@@ -706,14 +789,19 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
         }
         team_sync<L, W>(mask);
         if (z < sch.moves_per_point) continue;    // budget exhausted (loop ends) or a capped segment (loop goes on)
-        if (end_of_point<L, W, SPL, HAS_EXP>(P, chain, cs, tb, tid, warp, lane, mask)) break;
+        if (end_of_point<L, W, SPL, HAS_EXP>(P, smem, chain, team, tid, warp, lane, mask)) break;
     }
+#undef RING_NEXT32
+#undef RING_RESERVE
 
-    // chain state -> global memory
+    // chain state -> global memory: unread ring words go back to the cursors
     if (warp == 0) {
-        mt_ring_close(gM, tid, mask);
-        mt_ring_close(gS, tid, mask);
-        mt_ring_close(gR, tid, mask);
+        __syncwarp(mask);
+        if (tid == 0) {
+            mt_cursor_rewind(c->rng[STREAM_M], avM);
+            mt_cursor_rewind(c->rng[STREAM_S], avS);
+            mt_cursor_rewind(c->rng[STREAM_R], avR);
+        }
     }
     team_sync<L, W>(mask);
     {
@@ -722,7 +810,7 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
         for (int i = tid; i < (int)(sizeof(ChainCtrl) / 4); i += TPC) dst[i] = src[i];
         double *cg = P.com + (size_t)chain * sys.n_mol * 3;
         for (int i = tid; i < sys.n_mol * 3; i += TPC) cg[i] = com[i];
-        sites_to_global<TPC>(sites, P.sites + (size_t)chain * S * 3, sys, tid);
+        sites_to_global<TPC, Lay::NPOS>(sites, P.sites + (size_t)chain * S * 3, sys, tid);
     }
 }
 

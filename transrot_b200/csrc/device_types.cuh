@@ -77,9 +77,6 @@ struct KParams {
     long long max_moves;        // <= 0: run to completion
     long long trace_moves;
     int max_points, max_snaps;
-    // shared-memory layout (bytes)
-    int smem_tables;            // size of the per-block table region
-    int smem_per_chain;         // size of one chain's region
 };
 
 enum { STREAM_M = 0, STREAM_S = 1, STREAM_R = 2 };

@@ -169,6 +169,17 @@ __device__ __noinline__ int mt_ring_refill_words(uint32_t *mt, uint32_t *ring, M
     if (!load) gen = fed + count;
     fed += count;
     if (tl == 0) { cur->par = par; cur->gen = gen; cur->fed = fed; }
+    // pull the operands of the NEXT window towards L1 now: its refill then finds them there instead of
+    // waiting ~700 cycles on L2 with few other warps to cover the gap
+    if (tl < 4 && fed >= gen) {
+        const bool wrap = fed >= MT_N;                       // next window opens the next block
+        const uint32_t *o2 = wrap ? B : O;                   // its "old" block
+        const uint32_t *b2 = wrap ? O : B;                   // its "new" block (only [k-227] is read from it)
+        const int k2 = wrap ? 0 : fed;
+        const uint32_t *src = (tl < 2) ? o2 + k2 : ((k2 < MT_N - MT_M) ? o2 + k2 + MT_M : b2 + k2 + MT_M - MT_N);
+        src += (tl & 1) * 32;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+    }
     __syncwarp(mask);
     return count;
 }
@@ -253,6 +264,13 @@ __device__ __forceinline__ int mt_ring_next_int(MtRing &g, const FastMod &f, int
         if ((int)((uint32_t)bits - (uint32_t)val + (uint32_t)(n - 1)) >= 0) return val;
         mt_ring_reserve<L>(g, 1, tl, mask);
     }
+}
+
+// Give `avail` unread ring words back to the cursor so nothing but (par, gen, fed) has to persist.
+__device__ __forceinline__ void mt_cursor_rewind(MtCursor &c, int avail)
+{
+    if (avail <= c.fed) c.fed -= avail;
+    else { c.par ^= 1; c.fed = MT_N - (avail - c.fed); c.gen = MT_N; }   // back into the previous block
 }
 
 // Give the unread ring words back to the cursor so nothing but (par, gen, fed) has to persist.

@@ -175,24 +175,20 @@ __global__ void init_chains_kernel(InitParams ip)
 // Space.calcEnergy on supplied structures: one team per structure, the same device routine
 // the anneal kernel uses for write(n) / writeMovie energies.
 template <int L, int W, int SPL, bool HAS_EXP>
-__global__ void __launch_bounds__(Team<L, W>::TPC) total_energy_kernel(DevSystem sys, const double *sites_g, long long n, double *out, int smem_tables)
+__global__ void __launch_bounds__(Team<L, W>::TPC) total_energy_kernel(DevSystem sys, const double *sites_g, long long n, double *out)
 {
-    constexpr int TPC = Team<L, W>::TPC;
+    using Lay = Layout<L, W, SPL>;
+    constexpr int TPC = Lay::TPC;
     extern __shared__ __align__(16) unsigned char smem[];
-    load_tables(smem, sys);
-    const SmemTables tb = carve_tables(smem, sys);
-    ChainSmem *cs = (ChainSmem *)(smem + smem_tables);
-    SiteRec *sites = chain_sites(cs, sys);
+    Lay::load_tables(smem, sys);
+    ChainSmem *cs = Lay::chain(smem, 0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned mask = team_mask<L, W>();
     __syncthreads();
-    int info[SPL];
-#pragma unroll
-    for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
     for (long long i = blockIdx.x; i < n; i += gridDim.x) {
-        sites_from_global<TPC>(sites, sites_g + (size_t)i * sys.n_sites * 3, sys, tid);
+        sites_from_global<TPC, Lay::NPOS>(Lay::sites(cs), sites_g + (size_t)i * sys.n_sites * 3, sys, tid);
         __syncthreads();
-        const double e = team_total_energy<L, W, SPL, HAS_EXP>(sites, info, sys, tb, cs->part, tid, warp, lane, mask);
+        const double e = team_total_energy<L, W, SPL, HAS_EXP>(smem, cs, sys, tid, warp, lane, mask);
         if (tid == 0) out[i] = e;
         __syncthreads();
     }
@@ -202,32 +198,31 @@ __global__ void __launch_bounds__(Team<L, W>::TPC) total_energy_kernel(DevSystem
 // staging + move_energy + reduction path of the anneal kernel.
 template <int L, int W, int SPL, bool HAS_EXP>
 __global__ void __launch_bounds__(Team<L, W>::TPC) delta_energy_kernel(DevSystem sys, const double *sites_g, const int *mol, const double *trial,
-                                                                       long long n, double *e_start, double *e_end, double *d_e, int smem_tables)
+                                                                       long long n, double *e_start, double *e_end, double *d_e)
 {
-    constexpr int TPC = Team<L, W>::TPC;
+    using Lay = Layout<L, W, SPL>;
+    constexpr int TPC = Lay::TPC;
     extern __shared__ __align__(16) unsigned char smem[];
-    load_tables(smem, sys);
-    const SmemTables tb = carve_tables(smem, sys);
-    ChainSmem *cs = (ChainSmem *)(smem + smem_tables);
-    SiteRec *sites = chain_sites(cs, sys);
+    Lay::load_tables(smem, sys);
+    ChainSmem *cs = Lay::chain(smem, 0);
+    SiteRec *sites = Lay::sites(cs);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned mask = team_mask<L, W>();
-    const unsigned char *tab_cd = smem;
-    const unsigned char *tab_ab = smem + (sys.has_exp ? sys.n_types * sys.row_stride : 0);
+    const unsigned char *tab_cd = Lay::cd(smem), *tab_ab = Lay::ab(smem, sys);
     __syncthreads();
     int info[SPL];
 #pragma unroll
-    for (int k = 0; k < SPL; k++) info[k] = tb.pos_info[tid + k * TPC];
+    for (int k = 0; k < SPL; k++) info[k] = Lay::pos_info(smem, tid + k * TPC);
     for (long long i = blockIdx.x; i < n; i += gridDim.x) {
-        sites_from_global<TPC>(sites, sites_g + (size_t)i * sys.n_sites * 3, sys, tid);
+        sites_from_global<TPC, Lay::NPOS>(sites, sites_g + (size_t)i * sys.n_sites * 3, sys, tid);
         __syncthreads();
         const int m = mol[i];
-        const int off = tb.mol_off[m], sm = tb.mol_off[m + 1] - off;
+        const int off = Lay::mol_off(smem, m), sm = Lay::mol_off(smem, m + 1) - off;
         const double *tr_i = trial + (size_t)i * TR_MAX_MOL_SITES * 3;
         if (tid < sm) {
-            const int p = tb.site_pos[off + tid];
+            const int p = Lay::site_pos(smem, off + tid);
             const SiteRec r = sites[p];
-            const int inf = tb.pos_info[p];
+            const int inf = Lay::pos_info(smem, p);
             StageSite st;
             st.ox = r.x; st.oy = r.y; st.oz = r.z;
             st.nx = tr_i[3 * tid]; st.ny = tr_i[3 * tid + 1]; st.nz = tr_i[3 * tid + 2];

@@ -136,7 +136,6 @@ bool pick_variant(const tr_ctx *ctx, int n_sites, int tpc, Variant *out)
     return false;
 }
 
-int chains_per_block(const Variant &v) { return v.W == 1 ? 4 : 1; }
 bool same_variant(const Variant &a, const Variant &b) { return a.L == b.L && a.W == b.W && a.SPL == b.SPL; }
 
 // Site -> (thread, slot) permutation of a kernel variant: sites with Lennard-Jones parameters first, so that
@@ -165,20 +164,16 @@ int prepare_variant(tr_ctx *ctx, const Variant &v)
     return TR_OK;
 }
 
-int tables_bytes(const tr_ctx *ctx, const Variant &v)
-{
-    return smem_tables_bytes(ctx->sys.n_mol, ctx->sys.n_moveable, ctx->sys.n_types, ctx->sys.has_exp, ctx->sys.n_sites, v.tpc() * v.SPL);
-}
-
-int chain_bytes(const tr_ctx *ctx, const Variant &v) { return smem_chain_bytes(ctx->sys.n_mol, v.tpc() * v.SPL); }
-
 // ---- kernel dispatch -----------------------------------------------------------------------
 
 // Blocks per SM the register budget is squeezed for.  Half-warp teams: 7 x 64 threads = 28 chains per SM lets
 // 4096 chains be resident in one wave on 148 SMs with up to 146 registers per thread.
 template <int L, int W, int SPL> struct MinBlocks { static constexpr int value = 1; };
 template <int SPL> struct MinBlocks<16, 1, SPL> { static constexpr int value = 7; };
-template <> struct MinBlocks<32, 1, 2> { static constexpr int value = 4; };
+#ifndef TR_MINB_L32S2
+#define TR_MINB_L32S2 4
+#endif
+template <> struct MinBlocks<32, 1, 2> { static constexpr int value = TR_MINB_L32S2; };
 template <> struct MinBlocks<32, 1, 4> { static constexpr int value = 4; };
 template <> struct MinBlocks<32, 1, 6> { static constexpr int value = 3; };
 template <> struct MinBlocks<32, 4, 6> { static constexpr int value = 3; };
@@ -189,7 +184,7 @@ cudaError_t launch_anneal_lj(tr_ctx *ctx, const KParams &P)
 {
     constexpr int CPB = Team<L, W>::CPB;
     constexpr int MINB = MinBlocks<L, W, SPL>::value;
-    const int smem = P.smem_tables + CPB * P.smem_per_chain;
+    const int smem = Layout<L, W, SPL>::total_bytes(P.sys.n_types, HAS_EXP);
     const unsigned blocks = (unsigned)((P.n_chains + CPB - 1) / CPB);
     cudaError_t e;
     if (P.trace) {
@@ -219,27 +214,34 @@ cudaError_t launch_anneal_t(tr_ctx *ctx, const KParams &P)
 }
 
 template <int L, int W, int SPL, bool HAS_EXP>
-cudaError_t launch_total_t(tr_ctx *ctx, const double *d_sites, long long n, double *d_out, int smem_tables, int smem_chain)
+cudaError_t smem_need_t(tr_ctx *ctx, int *bytes)
+{
+    *bytes = Layout<L, W, SPL>::total_bytes(ctx->sys.n_types, HAS_EXP);
+    return cudaSuccess;
+}
+
+template <int L, int W, int SPL, bool HAS_EXP>
+cudaError_t launch_total_t(tr_ctx *ctx, const double *d_sites, long long n, double *d_out)
 {
     auto kern = total_energy_kernel<L, W, SPL, HAS_EXP>;
-    const int smem = smem_tables + smem_chain;
+    const int smem = Layout<L, W, SPL>::total_bytes(ctx->sys.n_types, HAS_EXP);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
-    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(ctx->sys, d_sites, n, d_out, smem_tables);
+    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(ctx->sys, d_sites, n, d_out);
     return cudaGetLastError();
 }
 
 template <int L, int W, int SPL, bool HAS_EXP>
 cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol, const double *d_trial, long long n,
-                           double *d_es, double *d_ee, double *d_de, int smem_tables, int smem_chain)
+                           double *d_es, double *d_ee, double *d_de)
 {
     auto kern = delta_energy_kernel<L, W, SPL, HAS_EXP>;
-    const int smem = smem_tables + smem_chain;
+    const int smem = Layout<L, W, SPL>::total_bytes(ctx->sys.n_types, HAS_EXP);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
-    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(ctx->sys, d_sites, d_mol, d_trial, n, d_es, d_ee, d_de, smem_tables);
+    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(ctx->sys, d_sites, d_mol, d_trial, n, d_es, d_ee, d_de);
     return cudaGetLastError();
 }
 
@@ -280,7 +282,14 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
                     ctx->threads_per_chain, TR_MAX_SITES);
     ctx->variant = v;
     if (int r = prepare_variant(ctx, v)) return r;
-    const int smem = tables_bytes(ctx, v) + chains_per_block(v) * chain_bytes(ctx, v);
+    int smem = 0;
+    {
+        cudaError_t e;
+#define CALL_SMEM(L, W, SPL, HE) smem_need_t<L, W, SPL, HE>(ctx, &smem)
+        TR_DISPATCH(v, ctx->sys.has_exp, CALL_SMEM);
+#undef CALL_SMEM
+        if (e != cudaSuccess) return fail(ctx, TR_ELIMIT, "Error: no kernel variant for this system");
+    }
     if (smem > ctx->max_smem_optin)
         return fail(ctx, TR_ELIMIT, "Error: system needs %d bytes of shared memory per block, device offers %d", smem,
                     ctx->max_smem_optin);
@@ -300,7 +309,7 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
     CK(ctx, ctx->d_ctrl.alloc(C));
     CK(ctx, ctx->d_sites.alloc(C * S * 3));
     CK(ctx, ctx->d_com.alloc(C * N * 3));
-    CK(ctx, ctx->d_mt.alloc(C * 3 * 2 * MT_N));
+    CK(ctx, ctx->d_mt.alloc(C * 3 * 2 * MT_N + 64));   // + slack for the look-ahead prefetch of the last stream
     CK(ctx, ctx->d_snap_energy.alloc(C * max_snaps));
     CK(ctx, ctx->d_snap_tooth.alloc(C * max_snaps));
     CK(ctx, cudaMemsetAsync(ctx->d_snap_tooth.p, 0xff, C * max_snaps * sizeof(int), ctx->stream));
@@ -628,8 +637,6 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     P.trace_moves = ctx->trace_moves;
     P.max_points = ctx->max_points;
     P.max_snaps = ctx->max_snaps;
-    P.smem_tables = tables_bytes(ctx, v);
-    P.smem_per_chain = chain_bytes(ctx, v);
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e;
 #define CALL_ANNEAL(L, W, SPL, HE) launch_anneal_t<L, W, SPL, HE>(ctx, P)
@@ -828,10 +835,8 @@ extern "C" int tr_total_energy(tr_ctx *ctx, const double *sites, int64_t n, doub
     CK(ctx, d_sites.alloc((size_t)n * S3));
     CK(ctx, d_out.alloc((size_t)n));
     CK(ctx, cudaMemcpyAsync(d_sites.p, sites, (size_t)n * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const int st = tables_bytes(ctx, v);
-    const int sc = chain_bytes(ctx, v);
     cudaError_t e;
-#define CALL_TOTAL(L, W, SPL, HE) launch_total_t<L, W, SPL, HE>(ctx, d_sites.p, n, d_out.p, st, sc)
+#define CALL_TOTAL(L, W, SPL, HE) launch_total_t<L, W, SPL, HE>(ctx, d_sites.p, n, d_out.p)
     TR_DISPATCH(v, ctx->sys.has_exp, CALL_TOTAL);
 #undef CALL_TOTAL
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: total-energy kernel launch failed: %s", cudaGetErrorString(e));
@@ -866,10 +871,8 @@ extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *
     CK(ctx, cudaMemcpyAsync(d_sites.p, sites, (size_t)n * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d_trial.p, trial, (size_t)n * T3 * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d_mol.p, mol, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    const int st = tables_bytes(ctx, v);
-    const int sc = chain_bytes(ctx, v);
     cudaError_t e;
-#define CALL_DELTA(L, W, SPL, HE) launch_delta_t<L, W, SPL, HE>(ctx, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, d_de.p, st, sc)
+#define CALL_DELTA(L, W, SPL, HE) launch_delta_t<L, W, SPL, HE>(ctx, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, d_de.p)
     TR_DISPATCH(v, ctx->sys.has_exp, CALL_DELTA);
 #undef CALL_DELTA
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: delta-energy kernel launch failed: %s", cudaGetErrorString(e));
@@ -889,7 +892,7 @@ extern "C" int tr_rng_words(tr_ctx *ctx, const int64_t *seeds, int64_t n, int32_
     DevBuf<long long> d_seeds;
     DevBuf<uint32_t> d_mt, d_out;
     CK(ctx, d_seeds.alloc((size_t)n));
-    CK(ctx, d_mt.alloc((size_t)n * 3 * 2 * MT_N));
+    CK(ctx, d_mt.alloc((size_t)n * 3 * 2 * MT_N + 64));
     CK(ctx, d_out.alloc((size_t)n * 3 * (size_t)k));
     CK(ctx, cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->threads_per_chain == 16) rng_words_kernel<16><<<(unsigned)((n + 3) / 4), 64, 0, ctx->stream>>>(d_seeds.p, n, k, d_mt.p, d_out.p);

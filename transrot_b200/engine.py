@@ -13,7 +13,7 @@ import numpy as np
 from .host import Config, System, TransRotError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtransrot_b200.so")
+LIB_PATH = os.environ.get("TR_LIB", os.path.join(_HERE, "libtransrot_b200.so"))
 
 TR_MAX_MOL_SITES = 16
 
