@@ -11,3 +11,4 @@ from .engine import (  # noqa: F401
     Engine, EXPORTED_SYMBOLS, LIB_PATH, MINIMUM_DTYPE, POINT_DTYPE, SCHEDULE_DTYPE, SUMMARY_DTYPE, TRACE_DTYPE,
     load_library, schedule_from_config,
 )
+from .sharding import chain_range, gather_minima, global_minimum, owner_of  # noqa: F401
