@@ -204,7 +204,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from transrot_b200 import Engine, MINIMUM_DTYPE
+    from transrot_b200 import Engine, MINIMUM_DTYPE, gather_minima, global_minimum
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,7 +230,6 @@ def run_ours(args):
     eng.set_schedules(cfg)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     minima_dev = torch.empty(cpg * MINIMUM_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-    gathered = torch.empty(world * cpg * MINIMUM_DTYPE.itemsize, dtype=torch.uint8, device="cuda") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -283,22 +282,18 @@ def run_ours(args):
         init(True)                                   # H2D seeds (+ propagate on the device)
         eng.run(0)
         eng.pack_minima_device(minima_dev.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, minima_dev)
-            allmin = gathered.cpu().numpy().view(MINIMUM_DTYPE)
-        else:
-            allmin = minima_dev.cpu().numpy().view(MINIMUM_DTYPE)
+        allmin = gather_minima(minima_dev, world)    # the only collective: NCCL all-gather of 24 B per chain
         s = eng.summary()
         pts = eng.points()
         se, st, _ = eng.snapshots(with_sites=False)
-        best = int(np.argmin(allmin["energy"]))
-        nbytes = allmin.nbytes + s.nbytes + pts.nbytes + se.nbytes + st.nbytes
-        if first <= int(allmin["chain"][best]) < first + cpg:       # the owner fetches the winning structure
-            x, e, t = eng.min_structure(int(allmin["chain"][best]) - first)
+        best = global_minimum(allmin)
+        nbytes = allmin.nbytes // world + s.nbytes + pts.nbytes + se.nbytes + st.nbytes
+        if first <= best[1] < first + cpg:           # the owner fetches the winning structure
+            x, e, t = eng.min_structure(best[1] - first)
             nbytes += x.nbytes
         torch.cuda.synchronize()
         d2h_holder["n"] = nbytes
-        d2h_holder["best"] = (float(allmin["energy"][best]), int(allmin["chain"][best]), int(allmin["tooth"][best]))
+        d2h_holder["best"] = best
         return (time.perf_counter() - t0) * 1e3
 
     e2e_step()   # one warm-up of the host path (allocations, pinned staging)
