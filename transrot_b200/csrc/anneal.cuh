@@ -218,7 +218,9 @@ struct Layout {
 // position) written operation by operation across the group, so that each dependent FP64 chain has
 // 2*NS - 1 independent instructions between its links (FP64 issues every 2 cycles per warp and a
 // dependent result is ready after ~8: a group of four saturates the pipe from a single warp).
-template <int NS, int MODE>
+// The first NLJ slots of the group take the MODE form (1: + Lennard-Jones, 2: + Born-Mayer), the rest are
+// Coulomb-only, so a Lennard-Jones slot and a bare-charge slot still share one interleaved group.
+template <int NS, int NLJ, int MODE>
 __device__ __forceinline__ void group_energy(const StageSite &st, const unsigned char *tab_cd, const unsigned char *tab_ab,
                                              const double *x, const double *y, const double *z, const double *qm, const int *col,
                                              double &eS, double &eE)
@@ -229,8 +231,8 @@ __device__ __forceinline__ void group_energy(const StageSite &st, const unsigned
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         kqq[s] = st.kq * qm[s];                              // kTimesQ * atom.q
-        if (MODE >= 1) cd[s] = *(const double2 *)(tab_cd + st.row + col[s]);
-        if (MODE >= 2) ab[s] = *(const double2 *)(tab_ab + st.row + col[s]);
+        if (MODE >= 1 && s < NLJ) cd[s] = *(const double2 *)(tab_cd + st.row + col[s]);
+        if (MODE >= 2 && s < NLJ) ab[s] = *(const double2 *)(tab_ab + st.row + col[s]);
     }
     {
         double dx[G], dy[G], dz[G];
@@ -260,22 +262,23 @@ __device__ __forceinline__ void group_energy(const StageSite &st, const unsigned
     for (int g = 0; g < G; g++) e[g] = y0[g] * e[g];
 #pragma unroll
     for (int g = 0; g < G; g++) ri[g] = fma(p[g], e[g], y0[g]);
-    if (MODE >= 1) {
-        double r6[G], lj[G];
+    if (MODE >= 1 && NLJ > 0) {
+        constexpr int GL = 2 * NLJ;
+        double r6[GL > 0 ? GL : 1], lj[GL > 0 ? GL : 1];
 #pragma unroll
-        for (int g = 0; g < G; g++) t[g] = ri[g] * ri[g];
+        for (int g = 0; g < GL; g++) t[g] = ri[g] * ri[g];
 #pragma unroll
-        for (int g = 0; g < G; g++) r6[g] = t[g] * t[g];
+        for (int g = 0; g < GL; g++) r6[g] = t[g] * t[g];
 #pragma unroll
-        for (int g = 0; g < G; g++) r6[g] = r6[g] * t[g];
+        for (int g = 0; g < GL; g++) r6[g] = r6[g] * t[g];
 #pragma unroll
-        for (int g = 0; g < G; g++) lj[g] = fma(cd[g / 2].y, r6[g], -cd[g / 2].x);      // D/r^6 - C
+        for (int g = 0; g < GL; g++) lj[g] = fma(cd[g / 2].y, r6[g], -cd[g / 2].x);      // D/r^6 - C
 #pragma unroll
-        for (int s = 0; s < NS; s++) { eS = fma(lj[2 * s], r6[2 * s], eS); eE = fma(lj[2 * s + 1], r6[2 * s + 1], eE); }
+        for (int s = 0; s < NLJ; s++) { eS = fma(lj[2 * s], r6[2 * s], eS); eE = fma(lj[2 * s + 1], r6[2 * s + 1], eE); }
     }
     if (MODE >= 2) {
 #pragma unroll
-        for (int s = 0; s < NS; s++) {
+        for (int s = 0; s < NLJ; s++) {
             eS = fma(ab[s].x, exp(-ab[s].y * (r2[2 * s] * ri[2 * s])), eS);
             eE = fma(ab[s].x, exp(-ab[s].y * (r2[2 * s + 1] * ri[2 * s + 1])), eE);
         }
@@ -294,14 +297,12 @@ __device__ __forceinline__ void stage_site_energy(const StageSite &st, const uns
 #pragma unroll
     for (int k = 0; k < SPL; k += 2) {
         if (k + 1 < SPL) {
-            if (k + 1 < LJN) group_energy<2, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
-            else if (k < LJN) {
-                group_energy<1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
-                group_energy<1, 0>(st, tab_cd, tab_ab, x + k + 1, y + k + 1, z + k + 1, qm + k + 1, col + k + 1, eS, eE);
-            } else group_energy<2, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            if (k + 1 < LJN) group_energy<2, 2, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            else if (k < LJN) group_energy<2, 1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            else group_energy<2, 0, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
         } else {
-            if (k < LJN) group_energy<1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
-            else group_energy<1, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            if (k < LJN) group_energy<1, 1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            else group_energy<1, 0, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
         }
     }
 }

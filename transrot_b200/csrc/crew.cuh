@@ -1,0 +1,847 @@
+// The annealing hot path, warp-specialised ("crew" kernel).  Same reference code as anneal.cuh:
+// Main.sawtoothAnneal (Main.java:177-263), Space.move / Space.rotate (Space.java:660-734),
+// Molecule.rotateTemp (Molecule.java:64-97), Atom.calcEnergy (Atom.java:91-119), Space.calcEnergy
+// (Space.java:648-658).
+//
+// Why.  In the team kernel (anneal.cuh) every lane of a chain's team executes the move's serial
+// control flow (ring draws, u -> double conversions, sincos, Metropolis exp, bookkeeping): ~500
+// issue slots per move that serve ONE chain, as many as the pair arithmetic itself (ncu: FP64 pipe
+// 38 % active, issue 53-68 %).  Here a block owns C chains and splits the work by warp role:
+//   * warp 0, the CONTROL warp: lane c runs chain c's control flow, so those instructions serve up
+//     to 32 chains at once.  Part A finishes the pending move (Metropolis test, commit, the
+//     sawtoothAnneal accumulators, end-of-point / end-of-tooth logic); part B draws the next move,
+//     builds the trial geometry of its s_m sites into the chain's staging area and posts a request.
+//   * warps 1..E, the ENERGY warps: warp-per-chain (lane = position mod 32).  For a posted move they
+//     evaluate the staged sites against their positions in FP64 and shuffle-reduce eEnd - eStart into
+//     the chain's mailbox; they keep the chain's three MT19937 rings topped up (>= 33 unread words per
+//     stream after every round, so the control lane never waits for the generator); and they serve the
+//     rare cooperative requests (Space.calcEnergy for write(n) / writeMovie, structure dumps).
+// Two named barriers per round separate the phases.  Several blocks per SM overlap one block's
+// control phase with another's energy phase.
+//
+// Shared memory per chain: CrewChain (ChainCtrl, schedule, rings, mailbox) + stage[max s_m] +
+// com[N][3] + x[NPOS] y[NPOS] z[NPOS] (SoA: an energy lane reads position lane + 32 k without bank
+// conflicts; charges and table columns are chain-independent and live in the energy lanes'
+// registers).  Positions are ordered Lennard-Jones sites first, as in anneal.cuh.
+#pragma once
+#include "anneal.cuh"
+
+namespace tr {
+
+enum { REQ_IDLE = 0, REQ_MOVE = 1, REQ_TOTAL = 2, REQ_SYNC = 3 };
+enum { CHAIN_ABORT_RNG = 2 };      // ChainCtrl.done: ring underflow inside a nextInt rejection loop (p < 1e-50 per move)
+
+struct __align__(16) CrewDesc {    // one posted move (Space.move / Space.rotate arguments after the draws)
+    double va, vb, vc;             // translation vector, or (sin, cos, -) of the rotation angle
+    int m, off, sm;                // particle, its first site, its site count
+    int rot;                       // 0 = Space.move, 1 = Space.rotate
+    int axis;                      // Molecule.java:68
+    int pad_[3];
+};
+
+struct __align__(16) CrewChain {
+    ChainCtrl ctrl;
+    tr_schedule sch;
+    uint32_t *mt;                  // global: [3][2][624] ping-pong blocks of this chain
+    uint32_t ring[3][MT_RING];
+    CrewDesc desc[2];              // the move posted this round and the one before it (still staged: commit source)
+    int wr[3];                     // words appended to each ring so far (energy warps)
+    int rd[3];                     // words consumed from each ring so far (control lane, published per round)
+    int req;                       // this round's request to the energy warps
+    int slot;                      // REQ_MOVE: which desc[] is the new move
+    int commit;                    // desc[] slot whose staged trial coordinates are to be committed first (setTemps), or -1
+    int snap_slot;                 // REQ_TOTAL: write(n) slot to dump the structure into, or -1
+    int oob;                       // REQ_MOVE result: rejected by the 0.75 * spaceLen box, no energy evaluated
+    int pad_;
+    double dE, eS, eE;             // REQ_MOVE results (eS, eE only when tracing)
+    double etot;                   // REQ_TOTAL result
+};
+
+constexpr int CREW_BAR = 1;        // named barrier used by both roles
+
+__device__ __forceinline__ void crew_bar(int nthreads) { asm volatile("bar.sync %0, %1;" ::"n"(CREW_BAR), "r"(nthreads) : "memory"); }
+
+// Chain-independent tables at compile-time offsets from the start of dynamic shared memory; the C
+// chain regions follow at a runtime stride.
+template <int SPL>
+struct CrewTables {
+    static constexpr int NPOS = 32 * SPL;
+    static constexpr int OFF_MOL_OFF = 16;                                       // [0..15]: block-wide scalars
+    static constexpr int OFF_MOVEABLE = OFF_MOL_OFF + align16((NPOS + 1) * 4);
+    static constexpr int OFF_SITE_POS = OFF_MOVEABLE + align16(NPOS * 4);
+    static constexpr int OFF_POS_INFO = OFF_SITE_POS + align16(NPOS * 4);
+    static constexpr int OFF_QPOS = OFF_POS_INFO + align16(NPOS * 4);
+    static constexpr int OFF_CD = OFF_QPOS + NPOS * 8;
+
+    __host__ __device__ static int table_bytes(int n_types, bool has_exp) { return (OFF_CD + n_types * (n_types + 1) * 16 * (has_exp ? 2 : 1) + 127) & ~127; }
+    // fixed part + stage + com + coordinates, padded to 16 mod 128 so that lanes of the control warp
+    // (one chain each) hit different banks when they touch the same field
+    __host__ __device__ static int chain_bytes(int n_mol, int max_mol_sites)
+    {
+        int b = align16((int)sizeof(CrewChain)) + max_mol_sites * (int)sizeof(StageSite) + align16(n_mol * 24) + NPOS * 24;
+        b = (b + 127) & ~127;
+        return b + 16;
+    }
+
+    __device__ static __forceinline__ int &alive(unsigned char *smem) { return *(int *)smem; }
+    __device__ static __forceinline__ int mol_off(const unsigned char *smem, int m) { return *(const int *)(smem + OFF_MOL_OFF + 4 * m); }
+    __device__ static __forceinline__ int moveable(const unsigned char *smem, int i) { return *(const int *)(smem + OFF_MOVEABLE + 4 * i); }
+    __device__ static __forceinline__ int site_pos(const unsigned char *smem, int i) { return *(const int *)(smem + OFF_SITE_POS + 4 * i); }
+    __device__ static __forceinline__ int pos_info(const unsigned char *smem, int p) { return *(const int *)(smem + OFF_POS_INFO + 4 * p); }
+    __device__ static __forceinline__ double qpos(const unsigned char *smem, int p) { return *(const double *)(smem + OFF_QPOS + 8 * p); }
+    __device__ static __forceinline__ const unsigned char *cd(const unsigned char *smem) { return smem + OFF_CD; }
+    __device__ static __forceinline__ const unsigned char *ab(const unsigned char *smem, const DevSystem &sys)
+    {
+        return smem + OFF_CD + (sys.has_exp ? sys.n_types * sys.row_stride : 0);
+    }
+
+    __device__ static void load(unsigned char *smem, const DevSystem &sys)
+    {
+        const int T = sys.n_types, tab = T * (T + 1) * 16;
+        double2 *cdp = (double2 *)(smem + OFF_CD), *abp = (double2 *)(smem + OFF_CD + tab);
+        for (int i = threadIdx.x; i < T * (T + 1); i += blockDim.x) {
+            const int r = i / (T + 1), c = i % (T + 1);
+            cdp[i] = (c < T) ? sys.pair_cd[r * T + c] : make_double2(0.0, 0.0);
+            if (sys.has_exp) abp[i] = (c < T) ? sys.pair_ab[r * T + c] : make_double2(0.0, 0.0);
+        }
+        int *mo = (int *)(smem + OFF_MOL_OFF), *mv = (int *)(smem + OFF_MOVEABLE);
+        int *sp = (int *)(smem + OFF_SITE_POS), *pi = (int *)(smem + OFF_POS_INFO);
+        double *qp = (double *)(smem + OFF_QPOS);
+        for (int i = threadIdx.x; i <= sys.n_mol; i += blockDim.x) mo[i] = sys.mol_off[i];
+        for (int i = threadIdx.x; i < sys.n_moveable; i += blockDim.x) mv[i] = sys.moveable[i];
+        for (int i = threadIdx.x; i < sys.n_sites; i += blockDim.x) sp[i] = sys.site_pos[i];
+        for (int i = threadIdx.x; i < NPOS; i += blockDim.x) {
+            pi[i] = sys.pos_info[i];
+            const int s = sys.pos_site[i];
+            qp[i] = s >= 0 ? sys.site_q[s] : 0.0;
+        }
+    }
+};
+
+// Pointers into one chain's region.
+struct CrewView {
+    CrewChain *cs;
+    StageSite *stage;
+    double *com, *xs, *ys, *zs;
+};
+
+template <int SPL>
+__device__ __forceinline__ CrewView crew_view(unsigned char *chains, int c, int stride, int n_mol, int max_mol_sites)
+{
+    constexpr int NPOS = 32 * SPL;
+    unsigned char *b = chains + (size_t)c * stride;
+    CrewView v;
+    v.cs = (CrewChain *)b;
+    b += align16((int)sizeof(CrewChain));
+    v.stage = (StageSite *)b;
+    b += max_mol_sites * (int)sizeof(StageSite);
+    v.com = (double *)b;
+    b += align16(n_mol * 24);
+    v.xs = (double *)b; v.ys = v.xs + NPOS; v.zs = v.ys + NPOS;
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double a)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+}
+
+// ---- energy-warp services -----------------------------------------------------------------------
+
+// Ring upkeep.  The control lane reads ahead of the published `rd` cursors while the energy warps append
+// behind `wr`, so a window is only ever appended when at most 32 words are unread (64-word rings).
+// crew_ring_begin picks the neediest stream and issues the global loads of its next window; the pair
+// arithmetic of the round then hides their L2 latency; crew_ring_end twists, tempers and appends.
+// Afterwards every stream is brought to >= CREW_RING_FLOOR unread words synchronously (rare).
+constexpr int CREW_RING_FLOOR = 24;
+
+__device__ __forceinline__ MtWindow crew_ring_begin(CrewChain *cs, int lane)
+{
+    int avail = 64;
+    if (lane < 3) avail = cs->wr[lane] - cs->rd[lane];
+    const int a0 = __shfl_sync(0xffffffffu, avail, 0), a1 = __shfl_sync(0xffffffffu, avail, 1), a2 = __shfl_sync(0xffffffffu, avail, 2);
+    int s = 0, amin = a0;
+    if (a1 < amin) { amin = a1; s = 1; }
+    if (a2 < amin) { amin = a2; s = 2; }
+    if (amin > 32) s = -1;
+    return mt_window_begin(cs->mt + (s < 0 ? 0 : s) * 2 * MT_N, &cs->ctrl.rng[s < 0 ? 0 : s], s, lane);
+}
+
+__device__ __forceinline__ void crew_ring_end(CrewChain *cs, const MtWindow &w, int lane)
+{
+    if (w.s >= 0) {
+        const int wr = cs->wr[w.s];
+        const int n = mt_window_end(w, cs->mt + w.s * 2 * MT_N, cs->ring[w.s], &cs->ctrl.rng[w.s], wr, lane);
+        if (lane == 0) cs->wr[w.s] = wr + n;
+        __syncwarp();
+    }
+    int avail = 64;
+    if (lane < 3) avail = cs->wr[lane] - cs->rd[lane];
+    unsigned need = __ballot_sync(0xffffffffu, avail < CREW_RING_FLOOR);
+    while (need) {
+        const int s = __ffs(need) - 1;
+        need &= need - 1;
+        int wr = cs->wr[s], have = wr - cs->rd[s];
+        do {
+            const int n = mt_ring_refill_words<32>(cs->mt + s * 2 * MT_N, cs->ring[s], &cs->ctrl.rng[s], wr, lane, 0xffffffffu);
+            wr += n; have += n;
+        } while (have <= 32);
+        if (lane == 0) cs->wr[s] = wr;
+        __syncwarp();
+    }
+}
+
+// Blocking fill to more than 32 unread words per stream (kernel prologue).
+__device__ __forceinline__ void crew_ring_fill(CrewChain *cs, int lane)
+{
+    for (int s = 0; s < 3; s++) {
+        int wr = cs->wr[s], have = wr - cs->rd[s];
+        while (have <= 32) {
+            const int n = mt_ring_refill_words<32>(cs->mt + s * 2 * MT_N, cs->ring[s], &cs->ctrl.rng[s], wr, lane, 0xffffffffu);
+            wr += n; have += n;
+        }
+        if (lane == 0) cs->wr[s] = wr;
+        __syncwarp();
+    }
+}
+
+// setTemps (Molecule.java:128-135) of the move staged in the previous round: its trial coordinates are still in
+// the staging area.  Lanes a < s_m take one site each; lane 0 moves the tracked centre of mass of a translation.
+template <int SPL>
+__device__ __forceinline__ void crew_commit(const unsigned char *smem, const CrewView &v, const CrewDesc &d, int lane)
+{
+    if (lane < d.sm) {
+        const int p = CrewTables<SPL>::site_pos(smem, d.off + lane);
+        const StageSite *st = &v.stage[lane];
+        v.xs[p] = st->nx; v.ys[p] = st->ny; v.zs[p] = st->nz;
+    }
+    if (lane == 0 && !d.rot) {          // m.x = m.tempx
+        v.com[3 * d.m] = __dadd_rn(v.com[3 * d.m], d.va);
+        v.com[3 * d.m + 1] = __dadd_rn(v.com[3 * d.m + 1], d.vb);
+        v.com[3 * d.m + 2] = __dadd_rn(v.com[3 * d.m + 2], d.vc);
+    }
+    __syncwarp();
+}
+
+// One posted move for one chain, whole warp: trial geometry of the s_m sites (lane a < s_m <-> site a) into the
+// staging area with the 0.75 * spaceLen box test (Space.java:663,706), then eEnd - eStart (Space.java:711-718).
+template <int SPL, int LJS, bool HAS_EXP, bool TRACE>
+__device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewView &v, const DevSystem &sys, const CrewDesc &d,
+                                          const int (&info)[SPL], const double (&q)[SPL], int lane)
+{
+    using TL = CrewTables<SPL>;
+    CrewChain *cs = v.cs;
+    const int m = d.m, sm = d.sm;
+    bool oob = false;
+    if (lane < sm) {
+        const int p = TL::site_pos(smem, d.off + lane);
+        const int inf = TL::pos_info(smem, p);
+        double ox = v.xs[p], oy = v.ys[p], oz = v.zs[p], tx, ty, tz;
+        if (d.rot) {
+            // Molecule.java:70-95, operation for operation, no contraction (va = sin, vb = cos)
+            const double cx = v.com[3 * m], cy = v.com[3 * m + 1], cz = v.com[3 * m + 2];
+            const double va = d.va, vb = d.vb, nsn = __dmul_rn(-1.0, d.va);
+            const double ax = __dsub_rn(ox, cx), ay = __dsub_rn(oy, cy), az = __dsub_rn(oz, cz);
+            if (d.axis == 0) {
+                tx = ax;
+                ty = __dadd_rn(__dmul_rn(vb, ay), __dmul_rn(va, az));
+                tz = __dadd_rn(__dmul_rn(nsn, ay), __dmul_rn(vb, az));
+            } else if (d.axis == 1) {
+                tx = __dsub_rn(__dmul_rn(vb, ax), __dmul_rn(va, az));
+                ty = ay;
+                tz = __dadd_rn(__dmul_rn(va, ax), __dmul_rn(vb, az));
+            } else {
+                tx = __dadd_rn(__dmul_rn(vb, ax), __dmul_rn(va, ay));
+                ty = __dadd_rn(__dmul_rn(nsn, ax), __dmul_rn(vb, ay));
+                tz = az;
+            }
+            // a.x += x: the committed coordinate keeps the (a.x - x) + x round trip even if the move is rejected
+            ox = __dadd_rn(ax, cx); oy = __dadd_rn(ay, cy); oz = __dadd_rn(az, cz);
+            v.xs[p] = ox; v.ys[p] = oy; v.zs[p] = oz;
+            tx = __dadd_rn(tx, cx); ty = __dadd_rn(ty, cy); tz = __dadd_rn(tz, cz);
+        } else {
+            tx = __dadd_rn(ox, d.va); ty = __dadd_rn(oy, d.vb); tz = __dadd_rn(oz, d.vc);
+        }
+        StageSite st;
+        st.ox = ox; st.oy = oy; st.oz = oz;
+        st.nx = tx; st.ny = ty; st.nz = tz;
+        st.kq = __dmul_rn(K_VALUE, TL::qpos(smem, p));
+        st.row = info_type(inf) * sys.row_stride; st.lj = info_lj(inf);
+        v.stage[lane] = st;
+        const double b = cs->ctrl.space_len * 0.75;      // t > L*0.75 || t < L*-0.75; the lower bound is the exact negative
+        oob = (fabs(tx) > b) | (fabs(ty) > b) | (fabs(tz) > b);
+    }
+    const bool any_oob = __any_sync(0xffffffffu, oob);
+    __syncwarp();                                           // staging stores before the broadcast reads below
+    if (any_oob) {
+        if (lane == 0) cs->oob = 1;
+        return;
+    }
+    const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
+    double x[SPL], y[SPL], z[SPL], qm[SPL];
+    int col[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; k++) {
+        const bool on = info_mol(info[k]) != m;
+        x[k] = on ? v.xs[lane + 32 * k] : FAR_AWAY; y[k] = v.ys[lane + 32 * k]; z[k] = v.zs[lane + 32 * k];
+        qm[k] = on ? q[k] : 0.0;
+        col[k] = on ? info_col(info[k]) : sys.zero_col;
+    }
+    double eS = 0.0, eE = 0.0;
+    for (int a = 0; a < sm; a++) {
+        const StageSite st = v.stage[a];
+        if (HAS_EXP) stage_site_energy<SPL, SPL, 2>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
+        else if (LJS > 0 && st.lj) stage_site_energy<SPL, LJS, 1>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
+        else stage_site_energy<SPL, 0, 0>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
+    }
+    // differenced per lane before the reduction (less cancellation than reducing the two ~100x larger sums)
+    const double dE = warp_sum(eE - eS);
+    if (TRACE) { eS = warp_sum(eS); eE = warp_sum(eE); }
+    if (lane == 0) {
+        cs->oob = 0;
+        cs->dE = dE;
+        if (TRACE) { cs->eS = eS; cs->eE = eE; }
+    }
+}
+
+// Space.calcEnergy (Space.java:648-658) of the chain's committed structure, whole warp.
+template <int SPL, bool HAS_EXP>
+__device__ __forceinline__ double crew_total_energy(const unsigned char *smem, const CrewView &v, const DevSystem &sys, const int (&info)[SPL],
+                                                    const double (&q)[SPL], int lane)
+{
+    using TL = CrewTables<SPL>;
+    const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
+    double x[SPL], y[SPL], z[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; k++) { x[k] = v.xs[lane + 32 * k]; y[k] = v.ys[lane + 32 * k]; z[k] = v.zs[lane + 32 * k]; }
+    double acc = 0.0;
+    for (int p = 0; p < TL::NPOS; p++) {
+        const int infi = TL::pos_info(smem, p);
+        if (!info_valid(infi)) continue;
+        const int mi = info_mol(infi), row = info_type(infi) * sys.row_stride;
+        const double xi = v.xs[p], yi = v.ys[p], zi = v.zs[p];
+        const double kqi = K_VALUE * TL::qpos(smem, p);
+#pragma unroll
+        for (int k = 0; k < SPL; k++) {
+            if (info_valid(info[k]) && mi < info_mol(info[k])) {
+                const double2 cd = *(const double2 *)(tab_cd + row + info_col(info[k]));
+                double2 ab = make_double2(0.0, 0.0);
+                if (HAS_EXP) ab = *(const double2 *)(tab_ab + row + info_col(info[k]));
+                acc = pair_accumulate<HAS_EXP ? 2 : 1>(acc, x[k] - xi, y[k] - yi, z[k] - zi, 0.0, kqi * q[k], cd, ab);
+            }
+        }
+    }
+    return warp_sum(acc);
+}
+
+// shared SoA (position order) <-> global [S][3] (site order), whole warp
+template <int SPL>
+__device__ __forceinline__ void crew_sites_to_global(const CrewView &v, double *dst, const DevSystem &sys, int lane)
+{
+#pragma unroll
+    for (int k = 0; k < SPL; k++) {
+        const int p = lane + 32 * k, i = sys.pos_site[p];
+        if (i >= 0) { dst[3 * i] = v.xs[p]; dst[3 * i + 1] = v.ys[p]; dst[3 * i + 2] = v.zs[p]; }
+    }
+}
+
+template <int SPL>
+__device__ __forceinline__ void crew_sites_from_global(const CrewView &v, const double *src, const DevSystem &sys, int lane)
+{
+#pragma unroll
+    for (int k = 0; k < SPL; k++) {
+        const int p = lane + 32 * k, i = sys.pos_site[p];
+        v.xs[p] = i >= 0 ? src[3 * i] : FAR_AWAY;
+        v.ys[p] = i >= 0 ? src[3 * i + 1] : FAR_AWAY;
+        v.zs[p] = i >= 0 ? src[3 * i + 2] : FAR_AWAY;
+    }
+}
+
+// ---- control-lane pieces ---------------------------------------------------------------------------
+
+// End of a point (Main.java:225-240) and, when it was the tooth's last one, end of the tooth (:242-257), for
+// the chain of this lane.  `etot` = Space.calcEnergy of the current structure when a REQ_TOTAL round
+// preceded the call (movie energy and write(x+1) see the same structure), else unused.
+// Returns with c->done set when the chain has finished.
+__device__ __noinline__ void crew_finish_point(const KParams &P, CrewChain *cs, long long chain, double etot, bool have_etot)
+{
+    ChainCtrl *c = &cs->ctrl;
+    const tr_schedule &sch = cs->sch;
+    const int numTeeth = sch.static_temp ? 1 : sch.num_teeth;   // Main.java:74-76
+    const double t = c->t;
+    const int pi = c->n_points;
+    bool movie = true;
+    if (sch.write_conf_heat_capacities && t < 0.005 && t > -0.005) movie = false;   // the `continue` at :228
+    double t_next = t;
+    if (movie) {
+        if (!sch.static_temp) t_next = __dsub_rn(t, c->delT);
+        if (t_next < 0.0) t_next = 0.0;
+    }
+    if (P.points && pi < P.max_points) {
+        tr_point_rec r;
+        r.tooth = c->x; r.point = c->y; r.accepted = c->accepted; r.total = c->total;
+        r.movie_written = movie ? 1 : 0; r.finale = c->isDoubleCycle;
+        r.temp = t; r.total_energy = c->totalE; r.total_squared_energy = c->totalSqE;
+        r.movie_energy = (movie && have_etot) ? etot : __longlong_as_double(0x7ff8000000000000LL);
+        P.points[chain * P.max_points + pi] = r;
+    }
+    c->n_points = pi + 1;
+    c->t = t_next;
+    c->y += 1; c->z = 0;
+    c->totalE = 0.0; c->totalSqE = 0.0;
+    if (c->y < c->ptsPerTooth) return;
+
+    const int x = c->x;
+    const bool start_finale = (x == numTeeth - 1) && !c->isDoubleCycle && sch.finale;
+    c->saveT = __dmul_rn(c->saveT, sch.temp_decrease_per_tooth);
+    c->t = c->saveT;
+    c->ptsPerTooth += sch.points_added_per_tooth;
+    if (start_finale) {
+        c->t = 0.0;
+        c->isDoubleCycle = 1;
+        c->maxD = __ddiv_rn(c->maxD, 100.0);
+        c->maxRot = __ddiv_rn(c->maxRot, 100.0);
+        c->probRot = 0.0; c->probTrans = 0.0;
+        // x-- then x++: the finale repeats the same tooth index
+    } else {
+        c->x = x + 1;
+    }
+    c->y = 0; c->accepted = 0; c->total = 0;
+    c->delT = c->t / (double)(c->ptsPerTooth - 1);
+    if (!start_finale) {
+        // write(x+1) (Space.java:550-623): energy + minimum tracking here, the structure was dumped by the energy warp
+        const int k = c->n_snaps;
+        if (k < P.max_snaps) {
+            P.snap_energy[chain * P.max_snaps + k] = etot;
+            P.snap_tooth[chain * P.max_snaps + k] = x + 1;
+        }
+        c->n_snaps = k + 1;
+        if (etot < c->min_energy) { c->min_energy = etot; c->min_tooth = x + 1; }
+        if (c->x >= numTeeth) c->done = 1;
+    }
+}
+
+// Does the point that just ended need Space.calcEnergy (movie frame energy or write(x+1))?  Sets the
+// dump slot for the energy warp.
+__device__ __forceinline__ bool crew_point_needs_total(const KParams &P, CrewChain *cs)
+{
+    const ChainCtrl *c = &cs->ctrl;
+    const tr_schedule &sch = cs->sch;
+    const int numTeeth = sch.static_temp ? 1 : sch.num_teeth;
+    const double t = c->t;
+    const bool movie = !(sch.write_conf_heat_capacities && t < 0.005 && t > -0.005);
+    const bool tooth_end = c->y + 1 >= c->ptsPerTooth;
+    const bool start_finale = tooth_end && (c->x == numTeeth - 1) && !c->isDoubleCycle && sch.finale;
+    const bool snap = tooth_end && !start_finale;
+    cs->snap_slot = (snap && P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
+    return snap || (movie && P.points != nullptr);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------
+
+// BitsStreamGenerator.nextDouble from its two words, ((long)(hi >>> 6) << 26 | lo >>> 6) * 2^-52, without an
+// integer-to-double conversion: 1 + u 2^-52 is exact in [1, 2), and so is the subtraction.
+__device__ __forceinline__ double crew_next_double(uint32_t hi, uint32_t lo)
+{
+    const unsigned long long u = ((unsigned long long)(hi >> 6) << 26) | (unsigned long long)(lo >> 6);
+    return __longlong_as_double((long long)(0x3ff0000000000000ULL | u)) - 1.0;
+}
+
+// What the M and R streams say about the next move (Main.java:199-213, Molecule.java:67-68), drawn ahead of
+// time: both are consumed at positions that do not depend on the outcome of the move in flight.
+struct CrewCommon {
+    double sn, cs;            // sin / cos of rotAmount, if the move turns out to be a rotation
+    int kindbit;              // r.nextDouble() >= 0.5
+    int magw_rot, magw_trans; // magwalk flag of a rotation / of a translation
+    int axis, nR;             // rotation axis, words it takes from R
+    bool ok;
+};
+
+// The S-stream part of a move starting at ring position `pos`: Space.randMolecule (Space.java:735-738) and, for a
+// translation, the three components (Space.java:694-696).
+struct CrewPick {
+    double va, vb, vc;
+    int m, off, sm, rot, nS;
+    bool ok;
+};
+
+template <int SPL, int LJS, bool HAS_EXP, bool TRACE, int EW, int MINB>
+__global__ void __launch_bounds__(32 * (1 + EW), MINB)
+crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, const int max_mol_sites)
+{
+    using TL = CrewTables<SPL>;
+    constexpr int NT = 32 * (1 + EW);
+    extern __shared__ __align__(16) unsigned char smem[];
+    const DevSystem &sys = P.sys;
+    TL::load(smem, sys);
+    unsigned char *chains = smem + TL::table_bytes(sys.n_types, sys.has_exp);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long chain0 = (long long)blockIdx.x * C;
+    const int nloc = (int)((P.n_chains - chain0 < C) ? P.n_chains - chain0 : C);
+
+    // chain state -> shared memory (every warp takes whole chains)
+    for (int c = warp; c < nloc; c += 1 + EW) {
+        const CrewView v = crew_view<SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
+        const long long ch = chain0 + c;
+        const int *src = (const int *)(P.ctrl + ch);
+        int *dst = (int *)&v.cs->ctrl;
+        for (int i = lane; i < (int)(sizeof(ChainCtrl) / 4); i += 32) dst[i] = src[i];
+        const double *cg = P.com + (size_t)ch * sys.n_mol * 3;
+        for (int i = lane; i < sys.n_mol * 3; i += 32) v.com[i] = cg[i];
+        crew_sites_from_global<SPL>(v, P.sites + (size_t)ch * sys.n_sites * 3, sys, lane);
+        __syncwarp();
+        if (lane == 0) {
+            v.cs->sch = P.sched[v.cs->ctrl.sched];
+            v.cs->mt = P.mt + (size_t)ch * 3 * 2 * MT_N;
+            v.cs->req = REQ_IDLE; v.cs->snap_slot = -1; v.cs->commit = -1; v.cs->slot = 0; v.cs->oob = 0;
+        }
+        if (lane < 3) { v.cs->wr[lane] = 0; v.cs->rd[lane] = 0; }
+        __syncwarp();
+        if (!v.cs->ctrl.done) crew_ring_fill(v.cs, lane);
+    }
+    __syncthreads();
+
+#ifdef TR_CREW_TIMING
+    long long tm_a = 0, tm_b = 0, tm_c = 0, tm_rounds = 0;
+#define TM(...) __VA_ARGS__
+#else
+#define TM(...)
+#endif
+    if (warp == 0) {
+        // ================================================================ control warp: lane c <-> chain c
+        const bool mine = lane < nloc;
+        const CrewView v = crew_view<SPL>(chains, mine ? lane : 0, stride, sys.n_mol, max_mol_sites);
+        CrewChain *cs = v.cs;
+        ChainCtrl *c = &cs->ctrl;
+        const tr_schedule &sch = cs->sch;
+        const long long chain = chain0 + lane;
+        const FastMod three = fastmod_make(3);
+        const int S = sys.n_sites;
+
+        // hot state in registers; everything else stays in c (shared memory)
+        double t = 0.0, kBt = 0.0, running = 0.0, totalE = 0.0, totalSqE = 0.0, maxD = 0.0, maxRot = 0.0, maxTmag = 0.0;
+        unsigned long long thr_rot = 0, thr_trans = 0;
+        int z = 0, mpp = 1;
+        int seg_moves = 0, seg_acc = 0, seg_eval = 0;            // since the last flush into c
+        unsigned seg_sm = 0, seg_sm2 = 0;                         // pair evaluations = 2 * (S * sum s_m - sum s_m^2)
+        int rdM = 0, rdS = 0, rdR = 0;                            // ring positions consumed so far
+        int wrM = 0, wrS = 0, wrR = 0;                            // snapshot of the producers' cursors, taken between barriers
+        long long budget = P.max_moves > 0 ? P.max_moves : 0x7fffffffffffffffLL;
+        bool live = mine && !c->done;
+        bool hot = false;
+        // pipeline state
+        bool inflight = false, pend_total = false, total_for_init = false, bk_pending = false;
+        int commit_pending = 0, last_slot = 0;
+        int cur_info = 0;                                        // move in flight: m | sm << 16 | rot << 21 | magwalk << 22 | (axis + 1) << 23
+        bool metro_ok = false, cand_ok = false;
+        double rnd = 0.0, thr = 0.0, grd = 0.0;                  // Metropolis draw of the move in flight and its dE threshold
+        CrewCommon cm; cm.sn = cm.cs = 0.0; cm.kindbit = cm.magw_rot = cm.magw_trans = 0; cm.axis = -1; cm.nR = 0; cm.ok = false;
+        CrewPick cA, cB;                                         // successor if no Metropolis double is drawn / if one is
+        cA.va = cA.vb = cA.vc = 0.0; cA.m = cA.off = cA.sm = cA.rot = cA.nS = 0; cA.ok = false;
+        cB = cA;
+        // deferred bookkeeping of the move that just finished
+        int bk_info = 0, bk_acc = 0, bk_drew = 0, bk_oob = 0;
+        double bk_dE = 0.0, bk_rnd = 0.0, bk_eS = 0.0, bk_eE = 0.0;
+
+        auto load_hot = [&]() {
+            t = c->t; kBt = __dmul_rn(BOLTZMANN_CONSTANT, c->t);
+            running = c->running; totalE = c->totalE; totalSqE = c->totalSqE;
+            maxD = c->maxD; maxRot = c->maxRot; maxTmag = __dmul_rn(c->maxD, sch.magwalk_factor_trans);
+            thr_rot = double_threshold52(c->probRot); thr_trans = double_threshold52(c->probTrans);
+            z = c->z; mpp = sch.moves_per_point; hot = true;
+            metro_ok = false; cand_ok = false;
+        };
+        auto flush_hot = [&]() {
+            c->z = z; c->running = running; c->totalE = totalE; c->totalSqE = totalSqE;
+            c->total += seg_moves;                 // total++ per move (Main.java:196)
+            c->accepted += seg_acc; c->accepted_all += seg_acc;
+            c->moves += seg_moves; c->evaluated += seg_eval;
+            c->pair_evals += 2LL * ((long long)S * seg_sm - seg_sm2);
+            seg_moves = seg_acc = seg_eval = 0; seg_sm = seg_sm2 = 0;
+        };
+        // Main.java:215-223 for the finished move
+        auto bookkeep = [&]() {
+            running = __dadd_rn(running, bk_acc ? bk_dE : 0.0);
+            if (!sch.static_temp || z > sch.eq_configs) {
+                totalE = __dadd_rn(totalE, running);
+                totalSqE = __dadd_rn(totalSqE, __dmul_rn(running, running));
+            }
+            seg_acc += bk_acc;
+            if (!bk_oob) {
+                const int sm = (bk_info >> 16) & 31;
+                seg_eval++; seg_sm += (unsigned)sm; seg_sm2 += (unsigned)(sm * sm);
+            }
+            if (TRACE) {
+                const long long idx = c->moves + seg_moves;
+                if (idx < P.trace_moves) {
+                    tr_trace_rec r;
+                    r.mol = bk_info & 0xffff; r.kind = (int8_t)((bk_info >> 21) & 1); r.magwalk = (int8_t)((bk_info >> 22) & 1);
+                    r.bounds = (int8_t)bk_oob; r.accepted = (int8_t)bk_acc; r.axis = ((bk_info >> 23) & 7) - 1; r.drew_rand = bk_drew;
+                    r.e_start = bk_eS; r.e_end = bk_eE; r.dE = bk_dE;
+                    r.rand = bk_drew ? bk_rnd : __longlong_as_double(0x7ff8000000000000LL);
+                    r.temp = t; r.running = running;
+                    P.trace[chain * P.trace_moves + idx] = r;
+                }
+            }
+            seg_moves++; z++;
+            if (seg_moves >= (1 << 20)) flush_hot();
+            bk_pending = false;
+        };
+        auto ringM = [&](int pos) { return cs->ring[STREAM_M][pos & (MT_RING - 1)]; };
+        auto ringS = [&](int pos) { return cs->ring[STREAM_S][pos & (MT_RING - 1)]; };
+        auto ringR = [&](int pos) { return cs->ring[STREAM_R][pos & (MT_RING - 1)]; };
+        // Main.java:199-213 + Molecule.java:67-68 at the current M / R positions (nothing is consumed here)
+        auto draw_common = [&]() {
+            cm.ok = false; cm.nR = 0; cm.axis = -1;
+            if (wrM - rdM < 4) return;
+            // r.nextDouble() >= 0.5 (Main.java:199) is the top bit of the first word; both words are consumed.
+            // The second double (:200 or :208) is compared as a 52-bit integer against ceil(prob * 2^52).
+            const uint32_t w0 = ringM(rdM);
+            const unsigned long long u2 = ((unsigned long long)(ringM(rdM + 2) >> 6) << 26) | (ringM(rdM + 3) >> 6);
+            cm.kindbit = (int)(w0 >> 31);
+            cm.magw_rot = (u2 >= thr_rot) ? 0 : 1;
+            cm.magw_trans = (u2 >= thr_trans) ? 0 : 1;
+            if (cm.kindbit) {
+                if (wrR - rdR < 3) return;
+                const double maxR = cm.magw_rot ? JAVA_TWO_PI : maxRot;
+                const double u = crew_next_double(ringR(rdR), ringR(rdR + 1));                       // Molecule.java:67
+                const double rotAmount = __dmul_rn(__dmul_rn(__dsub_rn(u, 0.5), 2.0), maxR);
+                int n = 2;
+                for (;;) {                                                                          // Molecule.java:68: nextInt(3)
+                    if (rdR + n >= wrR) return;
+                    const int bits = (int)(ringR(rdR + n) >> 1);
+                    n++;
+                    cm.axis = (int)fastmod(three, (uint32_t)bits);
+                    if ((int)((uint32_t)bits - (uint32_t)cm.axis + 2u) >= 0) break;
+                }
+                cm.nR = n;
+                sincos(rotAmount, &cm.sn, &cm.cs);
+            }
+            cm.ok = true;
+        };
+        auto draw_pick = [&](CrewPick &k, int pos) {
+            k.ok = false;
+            int p = pos, pick;                         // Space.java:736: r.nextInt(moveableMolecules.size())
+            const int n = (int)sys.pick_mod.n;
+            if ((n & -n) == n) {
+                if (p >= wrS) return;
+                pick = (int)(((long long)n * (long long)(ringS(p) >> 1)) >> 31);
+                p++;
+            } else for (;;) {
+                if (p >= wrS) return;
+                const int bits = (int)(ringS(p) >> 1);
+                p++;
+                pick = (int)fastmod(sys.pick_mod, (uint32_t)bits);
+                if ((int)((uint32_t)bits - (uint32_t)pick + (uint32_t)(n - 1)) >= 0) break;
+            }
+            k.m = TL::moveable(smem, pick);
+            k.off = TL::mol_off(smem, k.m);
+            k.sm = TL::mol_off(smem, k.m + 1) - k.off;
+            k.rot = (cm.kindbit && k.sm > 1) ? 1 : 0;
+            if (!k.rot) {
+                if (p + 6 > wrS) return;
+                const double maxT = cm.magw_trans ? maxTmag : maxD;
+                const double ux = crew_next_double(ringS(p), ringS(p + 1));                          // Space.java:694-696
+                const double uy = crew_next_double(ringS(p + 2), ringS(p + 3));
+                const double uz = crew_next_double(ringS(p + 4), ringS(p + 5));
+                k.va = __dsub_rn(__dmul_rn(__dmul_rn(ux, 2.0), maxT), maxT);
+                k.vb = __dsub_rn(__dmul_rn(__dmul_rn(uy, 2.0), maxT), maxT);
+                k.vc = __dsub_rn(__dmul_rn(__dmul_rn(uz, 2.0), maxT), maxT);
+                p += 6;
+            }
+            k.nS = p - pos;
+            k.ok = true;
+        };
+        // Hand a drawn move to the energy warps; the stream cursors move past its words.
+        auto post_move = [&](const CrewPick &k) {
+            last_slot ^= 1;
+            CrewDesc d;
+            d.m = k.m; d.off = k.off; d.sm = k.sm; d.rot = k.rot; d.axis = k.rot ? cm.axis : -1;
+            d.va = k.rot ? cm.sn : k.va; d.vb = k.rot ? cm.cs : k.vb; d.vc = k.rot ? 0.0 : k.vc;
+            d.pad_[0] = d.pad_[1] = d.pad_[2] = 0;
+            cs->desc[last_slot] = d;
+            cs->slot = last_slot;
+            cs->commit = commit_pending ? (last_slot ^ 1) : -1;
+            commit_pending = 0;
+            const int magwalk = k.rot ? cm.magw_rot : cm.magw_trans;
+            cur_info = k.m | (k.sm << 16) | (k.rot << 21) | (magwalk << 22) | ((d.axis + 1) << 23);
+            rdS += k.nS; rdM += 4; rdR += k.rot ? cm.nR : 0;
+            inflight = true; budget--;
+        };
+        if (live) load_hot();
+
+        for (;;) {
+            TM(const long long tm0 = clock64();)
+            // ------------------------------------------------ phase 1 (critical): results of the round that just ended
+            int req = REQ_IDLE;
+            if (live) {
+                wrM = cs->wr[STREAM_M]; wrS = cs->wr[STREAM_S]; wrR = cs->wr[STREAM_R];     // stable: the producers are parked
+                if (inflight) {
+                    // Metropolis: Space.java:668-689 / :711-733
+                    const int oob = cs->oob;
+                    const double dE = oob ? 0.0 : cs->dE;
+                    int acc = oob ? 0 : 1, drew = 0;
+                    if (!oob && dE > 0.0) {
+                        drew = 1;                                       // the double is drawn before the T == 0 test
+                        if (!metro_ok) rnd = crew_next_double(ringS(rdS), ringS(rdS + 1));
+                        if (t == 0.0) acc = 0;
+                        else if (metro_ok && dE > thr + grd) acc = 0;   // rand > exp(-dE / kT)  <=>  dE > -kT log(rand), decided
+                        else if (metro_ok && dE < thr - grd) acc = 1;   // away from the rounding noise of either form
+                        else {
+                            const double test = exp(__ddiv_rn(__dmul_rn(-1.0, dE), kBt));
+                            if (rnd > test) acc = 0;
+                        }
+                    }
+                    bk_info = cur_info; bk_acc = acc; bk_drew = drew; bk_oob = oob; bk_dE = dE; bk_rnd = rnd;
+                    if (TRACE) { bk_eS = oob ? 0.0 : cs->eS; bk_eE = oob ? 0.0 : cs->eE; }
+                    bk_pending = true;
+                    inflight = false; metro_ok = false;
+                    if (acc) commit_pending = 1;
+                    rdS += 2 * drew;
+                    if (cand_ok) {
+                        post_move(drew ? cB : cA);                      // successor drawn ahead of time
+                        req = REQ_MOVE;
+                    }
+                    cand_ok = false;
+                }
+                if (req == REQ_IDLE) {
+                    // -------------------------------------------- phase 2 (rare): everything that is not "next move of the same point"
+                    if (bk_pending) bookkeep();
+                    if (pend_total) {
+                        const double etot = cs->etot;
+                        pend_total = false;
+                        if (total_for_init) {
+                            // Main.java:64,71: write(0) and startingEnergy = calcEnergy()
+                            const int k = c->n_snaps;
+                            if (k < P.max_snaps) { P.snap_energy[chain * P.max_snaps + k] = etot; P.snap_tooth[chain * P.max_snaps + k] = 0; }
+                            c->n_snaps = k + 1;
+                            if (etot < c->min_energy) { c->min_energy = etot; c->min_tooth = 0; }
+                            c->start_energy = etot; c->running = etot; c->started = 1;
+                            c->delT = c->t / (double)(c->ptsPerTooth - 1);      // Main.java:188 for tooth 0
+                            total_for_init = false;
+                        } else {
+                            crew_finish_point(P, cs, chain, etot, true);
+                        }
+                        load_hot();
+                    }
+                    if (!c->done && !c->started) {
+                        req = REQ_TOTAL; pend_total = true; total_for_init = true;
+                        cs->snap_slot = (P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
+                    } else if (!c->done && z >= mpp) {
+                        // end of the point: with a calcEnergy round first when its result is needed
+                        flush_hot();
+                        if (crew_point_needs_total(P, cs)) { req = REQ_TOTAL; pend_total = true; }
+                        else {
+                            crew_finish_point(P, cs, chain, 0.0, false);
+                            load_hot();
+                        }
+                    }
+                    if (!c->done && req == REQ_IDLE && budget > 0) {
+                        draw_common();
+                        if (cm.ok) draw_pick(cA, rdS);
+                        if (cm.ok && cA.ok) { post_move(cA); req = REQ_MOVE; }
+                        else c->done = CHAIN_ABORT_RNG;         // a nextInt rejection loop ran past 24 ring words
+                    }
+                    if (req == REQ_IDLE && commit_pending) req = REQ_SYNC;      // parked with an accepted move not yet committed
+                    if (req == REQ_TOTAL || req == REQ_SYNC) {
+                        cs->commit = commit_pending ? last_slot : -1;
+                        commit_pending = 0;
+                    }
+                    if (c->done && req == REQ_IDLE) live = false;
+                }
+                cs->rd[STREAM_M] = rdM; cs->rd[STREAM_S] = rdS; cs->rd[STREAM_R] = rdR;
+                cs->req = req;
+            } else if (mine) cs->req = REQ_IDLE;
+            const unsigned any = __ballot_sync(0xffffffffu, req != REQ_IDLE);
+            if (lane == 0) TL::alive(smem) = (int)any;
+            TM(const long long tm1 = clock64(); tm_a += tm1 - tm0; tm_rounds++;)
+            crew_bar(NT);                                   // B1: requests posted
+            if (!any) break;
+            // ------------------------------------------------ phase 3: in the shadow of the energy phase
+            if (live) {
+                if (bk_pending) bookkeep();
+                if (inflight) {
+                    // the Metropolis double the move in flight will draw if dE > 0, and its threshold on dE
+                    if (wrS - rdS >= 2) {
+                        rnd = crew_next_double(ringS(rdS), ringS(rdS + 1));
+                        if (t != 0.0) {
+                            thr = __dmul_rn(-kBt, log(rnd));
+                            grd = (kBt + fabs(thr)) * 1e-11;
+                        }
+                        metro_ok = true;
+                    }
+                    // both possible successors, if the move in flight has one inside this point and this launch
+                    if (z + 1 < mpp && budget > 0) {
+                        draw_common();
+                        if (cm.ok) { draw_pick(cA, rdS); draw_pick(cB, rdS + 2); }
+                        cand_ok = cm.ok && cA.ok && cB.ok;
+                    }
+                }
+            }
+            TM(const long long tm2 = clock64(); tm_b += tm2 - tm1;)
+            crew_bar(NT);                                   // B2: results posted
+            TM(tm_c += clock64() - tm2;)
+        }
+        TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 control: rounds %lld critical %lld shadow(incl B1) %lld waitB2 %lld cycles/round\n", tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds, tm_c / tm_rounds);)
+        // park the chain: counters into c, unread ring words back to the stream cursors
+        if (mine) {
+            if (hot) flush_hot();
+            mt_cursor_rewind(c->rng[STREAM_M], cs->wr[STREAM_M] - rdM);
+            mt_cursor_rewind(c->rng[STREAM_S], cs->wr[STREAM_S] - rdS);
+            mt_cursor_rewind(c->rng[STREAM_R], cs->wr[STREAM_R] - rdR);
+        }
+    } else {
+        // ================================================================ energy warps: warp <-> chains
+        int info[SPL];
+        double q[SPL];
+#pragma unroll
+        for (int k = 0; k < SPL; k++) { info[k] = TL::pos_info(smem, lane + 32 * k); q[k] = TL::qpos(smem, lane + 32 * k); }
+        for (;;) {
+            crew_bar(NT);                                   // B1
+            if (TL::alive(smem) == 0) break;
+            TM(const long long tm0 = clock64(); tm_rounds++;)
+            for (int c = warp - 1; c < nloc; c += EW) {
+                const CrewView v = crew_view<SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
+                const int req = v.cs->req;
+                if (req == REQ_IDLE) continue;
+                TM(const long long tm1 = clock64();)
+                const MtWindow w = crew_ring_begin(v.cs, lane);          // loads fly while the move is evaluated
+                const int commit = v.cs->commit;
+                if (commit >= 0) crew_commit<SPL>(smem, v, v.cs->desc[commit], lane);
+                if (req == REQ_MOVE) crew_move<SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, v.cs->desc[v.cs->slot], info, q, lane);
+                else if (req == REQ_TOTAL) {
+                    const double e = crew_total_energy<SPL, HAS_EXP>(smem, v, sys, info, q, lane);
+                    if (lane == 0) v.cs->etot = e;
+                    const int k = v.cs->snap_slot;
+                    if (k >= 0)
+                        crew_sites_to_global<SPL>(v, P.snap_sites + ((size_t)(chain0 + c) * P.max_snaps + k) * (size_t)sys.n_sites * 3, sys, lane);
+                }
+                TM(const long long tm2 = clock64(); tm_a += tm2 - tm1;)
+                crew_ring_end(v.cs, w, lane);
+                TM(tm_b += clock64() - tm2;)
+            }
+            TM(tm_c += clock64() - tm0;)
+            crew_bar(NT);                                   // B2
+        }
+        TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 warp %d: rounds %lld busy %lld (work %lld ring_end %lld) cycles/round\n", warp, tm_rounds, tm_c / tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds);)
+    }
+    __syncthreads();
+
+    // chain state -> global memory
+    for (int c = warp; c < nloc; c += 1 + EW) {
+        const CrewView v = crew_view<SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
+        const long long ch = chain0 + c;
+        int *dst = (int *)(P.ctrl + ch);
+        const int *src = (const int *)&v.cs->ctrl;
+        for (int i = lane; i < (int)(sizeof(ChainCtrl) / 4); i += 32) dst[i] = src[i];
+        double *cg = P.com + (size_t)ch * sys.n_mol * 3;
+        for (int i = lane; i < sys.n_mol * 3; i += 32) cg[i] = v.com[i];
+        crew_sites_to_global<SPL>(v, P.sites + (size_t)ch * sys.n_sites * 3, sys, lane);
+    }
+#undef TM
+}
+
+}  // namespace tr

@@ -184,6 +184,59 @@ __device__ __noinline__ int mt_ring_refill_words(uint32_t *mt, uint32_t *ring, M
     return count;
 }
 
+// The same window, split so that the global loads can be in flight while the warp does other work
+// (crew.cuh): mt_window_begin issues the loads of the next <= 32 words, mt_window_end twists, stores,
+// tempers and appends them to the ring.  Whole warp (L = 32); `s` < 0 marks "nothing to do".
+struct MtWindow {
+    int s;               // stream, or -1
+    int par, gen, fed;   // cursor before the window (after the block switch, if one was due)
+    int count;
+    int load;            // words were generated earlier (imported state / rewound cursor): plain reload
+    uint32_t a, b, far;  // this lane's operands
+};
+
+__device__ __forceinline__ MtWindow mt_window_begin(uint32_t *mt, const MtCursor *cur, int s, int lane)
+{
+    MtWindow w;
+    w.s = s; w.par = 0; w.gen = 0; w.fed = 0; w.count = 0; w.load = 0; w.a = w.b = w.far = 0u;
+    if (s < 0) return w;
+    int par = cur->par, gen = cur->gen, fed = cur->fed;
+    if (fed >= MT_N) { par ^= 1; gen = 0; fed = 0; }
+    const uint32_t *B = mt + par * MT_N, *O = mt + (par ^ 1) * MT_N;
+    w.load = fed < gen;
+    const int limit = w.load ? gen : MT_N;
+    w.count = (limit - fed < 32) ? limit - fed : 32;
+    w.par = par; w.gen = gen; w.fed = fed;
+    if (lane < w.count) {
+        const int k = fed + lane;
+        if (w.load) w.a = B[k];
+        else {
+            w.a = O[k];
+            w.b = (k == MT_N - 1) ? B[0] : O[k + 1];
+            w.far = (k < MT_N - MT_M) ? O[k + MT_M] : B[k + MT_M - MT_N];
+        }
+    }
+    return w;
+}
+
+// Returns the number of words appended at ring slot `wr`.
+__device__ __forceinline__ int mt_window_end(const MtWindow &w, uint32_t *mt, uint32_t *ring, MtCursor *cur, int wr, int lane)
+{
+    if (w.s < 0) return 0;
+    if (lane < w.count) {
+        uint32_t v = w.a;
+        if (!w.load) {
+            const uint32_t y = (w.a & 0x80000000u) | (w.b & 0x7fffffffu);
+            v = w.far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            mt[w.par * MT_N + w.fed + lane] = v;
+        }
+        ring[(wr + lane) & (MT_RING - 1)] = mt_temper(v);
+    }
+    if (lane == 0) { cur->par = w.par; cur->gen = w.load ? w.gen : w.fed + w.count; cur->fed = w.fed + w.count; }
+    __syncwarp();
+    return w.count;
+}
+
 template <int L>
 __device__ __forceinline__ void mt_ring_refill(MtRing &g, int tl, unsigned mask)
 {

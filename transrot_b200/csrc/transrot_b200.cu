@@ -2,8 +2,10 @@
 // kernel dispatch.  No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -11,6 +13,7 @@
 
 #include "../../include/transrot_b200.h"
 #include "anneal.cuh"
+#include "crew.cuh"
 #include "setup_kernels.cuh"
 
 using namespace tr;
@@ -54,6 +57,7 @@ struct tr_ctx {
     bool have_run_time = false;
     int sm_count = 0;
     int max_smem_optin = 0;
+    int smem_per_sm = 0;
 
     // system
     bool have_system = false;
@@ -85,6 +89,8 @@ struct tr_ctx {
     DevBuf<tr_trace_rec> d_trace;
     int max_points = 0, max_snaps = 0;
     Variant variant{16, 1, 1};
+    bool use_crew = false;        // warp-specialised kernel (crew.cuh): automatic choice while a chain fits one warp
+    int crew_chains = 0;          // chains per block, 0 = automatic
 };
 
 namespace {
@@ -130,6 +136,7 @@ bool pick_variant(const tr_ctx *ctx, int n_sites, int tpc, Variant *out)
 {
     for (const Variant &v : kVariants) {
         if (tpc > 0 && v.tpc() != tpc) continue;
+        if (tpc == 0 && v.L != 32) continue;      // auto: the crew kernel's layout (32 lanes per chain), then a block per chain
         if (v.tpc() * v.SPL >= n_sites) { *out = v; return true; }
     }
     (void)ctx;
@@ -245,6 +252,110 @@ cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol,
     return cudaGetLastError();
 }
 
+// ---- crew kernel (crew.cuh): launch geometry and dispatch ---------------------------------------
+
+#ifndef TR_CREW_EW
+#define TR_CREW_EW 4          // energy warps per block
+#endif
+#ifndef TR_CREW_MINB
+#define TR_CREW_MINB 4        // blocks per SM the register budget is squeezed for
+#endif
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int SPL>
+void crew_sizes_t(const tr_ctx *ctx, int max_mol_sites, int *tables, int *stride)
+{
+    *tables = CrewTables<SPL>::table_bytes(ctx->sys.n_types, ctx->sys.has_exp != 0);
+    *stride = CrewTables<SPL>::chain_bytes(ctx->sys.n_mol, max_mol_sites);
+}
+
+int max_mol_sites_of(const tr_ctx *ctx)
+{
+    int m = 1;
+    for (size_t i = 0; i + 1 < ctx->h_mol_off.size(); i++) m = std::max(m, ctx->h_mol_off[i + 1] - ctx->h_mol_off[i]);
+    return m;
+}
+
+// Chains per block C, bytes per chain region and dynamic shared memory of the crew kernel.  C is chosen so
+// that the grid fills every SM with TR_CREW_BPS (default 4) co-resident blocks in ONE wave when the chains
+// fit; with more chains than that the grid simply runs in several waves.
+int crew_geometry(tr_ctx *ctx, long long n_chains, int *C, int *stride, int *smem)
+{
+    int tables = 0;
+    const int maxs = max_mol_sites_of(ctx);
+    switch (ctx->variant.SPL) {
+    case 2: crew_sizes_t<2>(ctx, maxs, &tables, stride); break;
+    case 4: crew_sizes_t<4>(ctx, maxs, &tables, stride); break;
+    case 6: crew_sizes_t<6>(ctx, maxs, &tables, stride); break;
+    default: return fail(ctx, TR_ELIMIT, "Error: no crew kernel for %d sites per lane", ctx->variant.SPL);
+    }
+    const int bps = std::max(1, env_int("TR_CREW_BPS", 4));
+    const int per_block = std::min(ctx->max_smem_optin, (ctx->smem_per_sm - 1024 * bps) / bps);
+    int c_fit = (per_block - tables) / *stride;
+    if (c_fit < 1) c_fit = (ctx->max_smem_optin - tables) / *stride;     // fewer co-resident blocks, but it runs
+    if (c_fit < 1)
+        return fail(ctx, TR_ELIMIT, "Error: one chain needs %d bytes of shared memory, device offers %d", tables + *stride,
+                    ctx->max_smem_optin);
+    const long long slots = (long long)ctx->sm_count * bps;
+    int c = (int)std::min<long long>((n_chains + slots - 1) / slots, 32);
+    c = std::max(1, std::min(c, c_fit));
+    const int forced = ctx->crew_chains > 0 ? ctx->crew_chains : env_int("TR_CREW_C", 0);
+    if (forced > 0) c = std::max(1, std::min(std::min(forced, 32), (ctx->max_smem_optin - tables) / *stride));
+    *C = c;
+    *smem = tables + c * *stride;
+    return TR_OK;
+}
+
+template <int SPL, int LJS, bool HAS_EXP>
+cudaError_t launch_crew_lj(tr_ctx *ctx, const KParams &P, int C, int stride, int smem, int maxs)
+{
+    constexpr int EW = TR_CREW_EW;
+    const unsigned blocks = (unsigned)((P.n_chains + C - 1) / C);
+    cudaError_t e;
+    if (P.trace) {
+        auto kern = crew_kernel<SPL, SPL, HAS_EXP, true, EW, 1>;        // tracing: one generic variant
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+        kern<<<blocks, 32 * (1 + EW), smem, ctx->stream>>>(P, C, stride, maxs);
+    } else {
+        auto kern = crew_kernel<SPL, LJS, HAS_EXP, false, EW, TR_CREW_MINB>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+        kern<<<blocks, 32 * (1 + EW), smem, ctx->stream>>>(P, C, stride, maxs);
+    }
+    return cudaGetLastError();
+}
+
+template <int SPL, bool HAS_EXP>
+cudaError_t launch_crew_t(tr_ctx *ctx, const KParams &P, int C, int stride, int smem, int maxs)
+{
+    constexpr int THIRD = (SPL + 2) / 3 < 1 ? 1 : (SPL + 2) / 3;
+    const int lj_slots = (P.sys.n_lj_pos + 31) / 32;
+    if (HAS_EXP) return launch_crew_lj<SPL, SPL, HAS_EXP>(ctx, P, C, stride, smem, maxs);
+    if (lj_slots == 0) return launch_crew_lj<SPL, 0, HAS_EXP>(ctx, P, C, stride, smem, maxs);
+    if (lj_slots <= THIRD) return launch_crew_lj<SPL, THIRD, HAS_EXP>(ctx, P, C, stride, smem, maxs);
+    return launch_crew_lj<SPL, SPL, HAS_EXP>(ctx, P, C, stride, smem, maxs);
+}
+
+int launch_crew(tr_ctx *ctx, const KParams &P)
+{
+    int C = 0, stride = 0, smem = 0;
+    if (int r = crew_geometry(ctx, P.n_chains, &C, &stride, &smem)) return r;
+    const int maxs = max_mol_sites_of(ctx);
+    cudaError_t e = cudaErrorInvalidValue;
+    const bool he = ctx->sys.has_exp != 0;
+    switch (ctx->variant.SPL) {
+    case 2: e = he ? launch_crew_t<2, true>(ctx, P, C, stride, smem, maxs) : launch_crew_t<2, false>(ctx, P, C, stride, smem, maxs); break;
+    case 4: e = he ? launch_crew_t<4, true>(ctx, P, C, stride, smem, maxs) : launch_crew_t<4, false>(ctx, P, C, stride, smem, maxs); break;
+    case 6: e = he ? launch_crew_t<6, true>(ctx, P, C, stride, smem, maxs) : launch_crew_t<6, false>(ctx, P, C, stride, smem, maxs); break;
+    }
+    if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: crew kernel launch failed: %s", cudaGetErrorString(e));
+    return TR_OK;
+}
+
 #define TR_DISPATCH_CASES(CALL, HE)                                   \
     switch (key__) {                                                  \
     case 160101: e = CALL(16, 1, 1, HE); break;                       \
@@ -281,9 +392,13 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
         return fail(ctx, TR_ELIMIT, "Error: %d sites do not fit %d threads per chain (limit %d sites)", ctx->sys.n_sites,
                     ctx->threads_per_chain, TR_MAX_SITES);
     ctx->variant = v;
+    ctx->use_crew = ctx->threads_per_chain == 0 && v.W == 1;
     if (int r = prepare_variant(ctx, v)) return r;
     int smem = 0;
-    {
+    if (ctx->use_crew) {
+        int C = 0, stride = 0;
+        if (int r = crew_geometry(ctx, n_chains, &C, &stride, &smem)) return r;
+    } else {
         cudaError_t e;
 #define CALL_SMEM(L, W, SPL, HE) smem_need_t<L, W, SPL, HE>(ctx, &smem)
         TR_DISPATCH(v, ctx->sys.has_exp, CALL_SMEM);
@@ -378,6 +493,7 @@ extern "C" int tr_create(int device, tr_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    ctx->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
         delete ctx;
@@ -638,11 +754,15 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     P.max_points = ctx->max_points;
     P.max_snaps = ctx->max_snaps;
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e;
+    if (ctx->use_crew) {
+        if (int r = launch_crew(ctx, P)) return r;
+    } else {
+        cudaError_t e;
 #define CALL_ANNEAL(L, W, SPL, HE) launch_anneal_t<L, W, SPL, HE>(ctx, P)
-    TR_DISPATCH(v, ctx->sys.has_exp, CALL_ANNEAL);
+        TR_DISPATCH(v, ctx->sys.has_exp, CALL_ANNEAL);
 #undef CALL_ANNEAL
-    if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: anneal kernel launch failed: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: anneal kernel launch failed: %s", cudaGetErrorString(e));
+    }
     ctx->launches++;
     CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->have_run_time = true;
