@@ -63,9 +63,9 @@ __device__ __forceinline__ void crew_bar(int nthreads) { asm volatile("bar.sync 
 
 // Chain-independent tables at compile-time offsets from the start of dynamic shared memory; the C
 // chain regions follow at a runtime stride.
-template <int SPL>
+template <int L, int SPL>
 struct CrewTables {
-    static constexpr int NPOS = 32 * SPL;
+    static constexpr int NPOS = L * SPL;
     static constexpr int OFF_MOL_OFF = 16;                                       // [0..15]: block-wide scalars
     static constexpr int OFF_MOVEABLE = OFF_MOL_OFF + align16((NPOS + 1) * 4);
     static constexpr int OFF_SITE_POS = OFF_MOVEABLE + align16(NPOS * 4);
@@ -125,10 +125,10 @@ struct CrewView {
     double *com, *xs, *ys, *zs;
 };
 
-template <int SPL>
+template <int L, int SPL>
 __device__ __forceinline__ CrewView crew_view(unsigned char *chains, int c, int stride, int n_mol, int max_mol_sites)
 {
-    constexpr int NPOS = 32 * SPL;
+    constexpr int NPOS = L * SPL;
     unsigned char *b = chains + (size_t)c * stride;
     CrewView v;
     v.cs = (CrewChain *)b;
@@ -141,102 +141,156 @@ __device__ __forceinline__ CrewView crew_view(unsigned char *chains, int c, int 
     return v;
 }
 
-__device__ __forceinline__ double warp_sum(double a)
+// Sum over the L lanes of a team (a whole warp or one half of it); every lane gets the same bits.
+template <int L>
+__device__ __forceinline__ double crew_team_sum(double a, unsigned mask)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    for (int o = L / 2; o > 0; o >>= 1) a += __shfl_xor_sync(mask, a, o);
     return a;
 }
 
 // ---- energy-warp services -----------------------------------------------------------------------
 
-// Ring upkeep.  The control lane reads ahead of the published `rd` cursors while the energy warps append
+// Ring upkeep.  The control lane reads ahead of the published `rd` cursors while the energy teams append
 // behind `wr`, so a window is only ever appended when at most 32 words are unread (64-word rings).
 // crew_ring_begin picks the neediest stream and issues the global loads of its next window; the pair
 // arithmetic of the round then hides their L2 latency; crew_ring_end twists, tempers and appends.
 // Afterwards every stream is brought to >= CREW_RING_FLOOR unread words synchronously (rare).
+// A team of L = 16 lanes takes two words of the window per lane.
 constexpr int CREW_RING_FLOOR = 24;
 
-__device__ __forceinline__ MtWindow crew_ring_begin(CrewChain *cs, int lane)
+template <int L>
+struct CrewWindow {
+    int s, par, gen, fed, count, load, wr;
+    uint32_t a[32 / L], b[32 / L], far[32 / L];
+};
+
+template <int L>
+__device__ __forceinline__ CrewWindow<L> crew_ring_begin(CrewChain *cs, int tl)
 {
-    int avail = 64;
-    if (lane < 3) avail = cs->wr[lane] - cs->rd[lane];
-    const int a0 = __shfl_sync(0xffffffffu, avail, 0), a1 = __shfl_sync(0xffffffffu, avail, 1), a2 = __shfl_sync(0xffffffffu, avail, 2);
-    int s = 0, amin = a0;
-    if (a1 < amin) { amin = a1; s = 1; }
-    if (a2 < amin) { amin = a2; s = 2; }
-    if (amin > 32) s = -1;
-    return mt_window_begin(cs->mt + (s < 0 ? 0 : s) * 2 * MT_N, &cs->ctrl.rng[s < 0 ? 0 : s], s, lane);
+    CrewWindow<L> w;
+    const int aM = cs->wr[0] - cs->rd[0], aS = cs->wr[1] - cs->rd[1], aR = cs->wr[2] - cs->rd[2];
+    int s = 0, amin = aM;
+    if (aS < amin) { amin = aS; s = 1; }
+    if (aR < amin) { amin = aR; s = 2; }
+    w.s = amin > 32 ? -1 : s;
+    w.par = w.gen = w.fed = w.count = w.load = w.wr = 0;
+#pragma unroll
+    for (int j = 0; j < 32 / L; j++) w.a[j] = w.b[j] = w.far[j] = 0u;
+    if (w.s < 0) return w;
+    const MtCursor cur = cs->ctrl.rng[s];
+    uint32_t *mt = cs->mt + s * 2 * MT_N;
+    int par = cur.par, gen = cur.gen, fed = cur.fed;
+    if (fed >= MT_N) { par ^= 1; gen = 0; fed = 0; }
+    const uint32_t *B = mt + par * MT_N, *O = mt + (par ^ 1) * MT_N;
+    w.load = fed < gen;
+    const int limit = w.load ? gen : MT_N;
+    w.count = (limit - fed < 32) ? limit - fed : 32;
+    w.par = par; w.gen = gen; w.fed = fed; w.wr = cs->wr[s];
+#pragma unroll
+    for (int j = 0; j < 32 / L; j++) {
+        const int i = tl + j * L;
+        if (i < w.count) {
+            const int k = fed + i;
+            if (w.load) w.a[j] = B[k];
+            else {
+                w.a[j] = O[k];
+                w.b[j] = (k == MT_N - 1) ? B[0] : O[k + 1];
+                w.far[j] = (k < MT_N - MT_M) ? O[k + MT_M] : B[k + MT_M - MT_N];
+            }
+        }
+    }
+    return w;
 }
 
-__device__ __forceinline__ void crew_ring_end(CrewChain *cs, const MtWindow &w, int lane)
+template <int L>
+__device__ __forceinline__ void crew_ring_end(CrewChain *cs, const CrewWindow<L> &w, int tl, unsigned mask)
 {
     if (w.s >= 0) {
-        const int wr = cs->wr[w.s];
-        const int n = mt_window_end(w, cs->mt + w.s * 2 * MT_N, cs->ring[w.s], &cs->ctrl.rng[w.s], wr, lane);
-        if (lane == 0) cs->wr[w.s] = wr + n;
-        __syncwarp();
+        uint32_t *mt = cs->mt + w.s * 2 * MT_N;
+#pragma unroll
+        for (int j = 0; j < 32 / L; j++) {
+            const int i = tl + j * L;
+            if (i < w.count) {
+                uint32_t v = w.a[j];
+                if (!w.load) {
+                    const uint32_t y = (w.a[j] & 0x80000000u) | (w.b[j] & 0x7fffffffu);
+                    v = w.far[j] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                    mt[w.par * MT_N + w.fed + i] = v;
+                }
+                cs->ring[w.s][(w.wr + i) & (MT_RING - 1)] = mt_temper(v);
+            }
+        }
+        if (tl == 0) {
+            MtCursor c;
+            c.par = w.par; c.gen = w.load ? w.gen : w.fed + w.count; c.fed = w.fed + w.count;
+            cs->ctrl.rng[w.s] = c;
+            cs->wr[w.s] = w.wr + w.count;
+        }
+        __syncwarp(mask);
     }
-    int avail = 64;
-    if (lane < 3) avail = cs->wr[lane] - cs->rd[lane];
-    unsigned need = __ballot_sync(0xffffffffu, avail < CREW_RING_FLOOR);
-    while (need) {
-        const int s = __ffs(need) - 1;
-        need &= need - 1;
-        int wr = cs->wr[s], have = wr - cs->rd[s];
-        do {
-            const int n = mt_ring_refill_words<32>(cs->mt + s * 2 * MT_N, cs->ring[s], &cs->ctrl.rng[s], wr, lane, 0xffffffffu);
-            wr += n; have += n;
-        } while (have <= 32);
-        if (lane == 0) cs->wr[s] = wr;
-        __syncwarp();
+    const int aM = cs->wr[0] - cs->rd[0], aS = cs->wr[1] - cs->rd[1], aR = cs->wr[2] - cs->rd[2];
+    if (aM < CREW_RING_FLOOR || aS < CREW_RING_FLOOR || aR < CREW_RING_FLOOR) {
+        for (int s = 0; s < 3; s++) {
+            int wr = cs->wr[s], have = wr - cs->rd[s];
+            if (have >= CREW_RING_FLOOR) continue;
+            do {
+                const int n = mt_ring_refill_words<L>(cs->mt + s * 2 * MT_N, cs->ring[s], &cs->ctrl.rng[s], wr, tl, mask);
+                wr += n; have += n;
+            } while (have <= 32);
+            if (tl == 0) cs->wr[s] = wr;
+            __syncwarp(mask);
+        }
     }
 }
 
 // Blocking fill to more than 32 unread words per stream (kernel prologue).
-__device__ __forceinline__ void crew_ring_fill(CrewChain *cs, int lane)
+template <int L>
+__device__ __forceinline__ void crew_ring_fill(CrewChain *cs, int tl, unsigned mask)
 {
     for (int s = 0; s < 3; s++) {
         int wr = cs->wr[s], have = wr - cs->rd[s];
         while (have <= 32) {
-            const int n = mt_ring_refill_words<32>(cs->mt + s * 2 * MT_N, cs->ring[s], &cs->ctrl.rng[s], wr, lane, 0xffffffffu);
+            const int n = mt_ring_refill_words<L>(cs->mt + s * 2 * MT_N, cs->ring[s], &cs->ctrl.rng[s], wr, tl, mask);
             wr += n; have += n;
         }
-        if (lane == 0) cs->wr[s] = wr;
-        __syncwarp();
+        if (tl == 0) cs->wr[s] = wr;
+        __syncwarp(mask);
     }
 }
 
 // setTemps (Molecule.java:128-135) of the move staged in the previous round: its trial coordinates are still in
 // the staging area.  Lanes a < s_m take one site each; lane 0 moves the tracked centre of mass of a translation.
-template <int SPL>
-__device__ __forceinline__ void crew_commit(const unsigned char *smem, const CrewView &v, const CrewDesc &d, int lane)
+template <int L, int SPL>
+__device__ __forceinline__ void crew_commit(const unsigned char *smem, const CrewView &v, const CrewDesc &d, int tl, unsigned mask)
 {
-    if (lane < d.sm) {
-        const int p = CrewTables<SPL>::site_pos(smem, d.off + lane);
-        const StageSite *st = &v.stage[lane];
+    if (tl < d.sm) {
+        const int p = CrewTables<L, SPL>::site_pos(smem, d.off + tl);
+        const StageSite *st = &v.stage[tl];
         v.xs[p] = st->nx; v.ys[p] = st->ny; v.zs[p] = st->nz;
     }
-    if (lane == 0 && !d.rot) {          // m.x = m.tempx
+    if (tl == 0 && !d.rot) {          // m.x = m.tempx
         v.com[3 * d.m] = __dadd_rn(v.com[3 * d.m], d.va);
         v.com[3 * d.m + 1] = __dadd_rn(v.com[3 * d.m + 1], d.vb);
         v.com[3 * d.m + 2] = __dadd_rn(v.com[3 * d.m + 2], d.vc);
     }
-    __syncwarp();
+    __syncwarp(mask);
 }
 
-// One posted move for one chain, whole warp: trial geometry of the s_m sites (lane a < s_m <-> site a) into the
+// One posted move for one chain, one team: trial geometry of the s_m sites (lane a < s_m <-> site a) into the
 // staging area with the 0.75 * spaceLen box test (Space.java:663,706), then eEnd - eStart (Space.java:711-718).
-template <int SPL, int LJS, bool HAS_EXP, bool TRACE>
+template <int L, int SPL, int LJS, bool HAS_EXP, bool TRACE>
 __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewView &v, const DevSystem &sys, const CrewDesc &d,
-                                          const int (&info)[SPL], const double (&q)[SPL], int lane)
+                                          const int (&info)[SPL], const double (&q)[SPL], int tl, unsigned mask)
 {
-    using TL = CrewTables<SPL>;
+    using TL = CrewTables<L, SPL>;
+    static_assert(TR_MAX_MOL_SITES <= L, "one lane per site of the moved particle");
     CrewChain *cs = v.cs;
     const int m = d.m, sm = d.sm;
     bool oob = false;
-    if (lane < sm) {
-        const int p = TL::site_pos(smem, d.off + lane);
+    if (tl < sm) {
+        const int p = TL::site_pos(smem, d.off + tl);
         const int inf = TL::pos_info(smem, p);
         double ox = v.xs[p], oy = v.ys[p], oz = v.zs[p], tx, ty, tz;
         if (d.rot) {
@@ -269,14 +323,14 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
         st.nx = tx; st.ny = ty; st.nz = tz;
         st.kq = __dmul_rn(K_VALUE, TL::qpos(smem, p));
         st.row = info_type(inf) * sys.row_stride; st.lj = info_lj(inf);
-        v.stage[lane] = st;
+        v.stage[tl] = st;
         const double b = cs->ctrl.space_len * 0.75;      // t > L*0.75 || t < L*-0.75; the lower bound is the exact negative
         oob = (fabs(tx) > b) | (fabs(ty) > b) | (fabs(tz) > b);
     }
-    const bool any_oob = __any_sync(0xffffffffu, oob);
-    __syncwarp();                                           // staging stores before the broadcast reads below
+    const bool any_oob = (__ballot_sync(mask, oob) & mask) != 0u;
+    __syncwarp(mask);                                       // staging stores before the broadcast reads below
     if (any_oob) {
-        if (lane == 0) cs->oob = 1;
+        if (tl == 0) cs->oob = 1;
         return;
     }
     const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
@@ -285,7 +339,7 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
 #pragma unroll
     for (int k = 0; k < SPL; k++) {
         const bool on = info_mol(info[k]) != m;
-        x[k] = on ? v.xs[lane + 32 * k] : FAR_AWAY; y[k] = v.ys[lane + 32 * k]; z[k] = v.zs[lane + 32 * k];
+        x[k] = on ? v.xs[tl + L * k] : FAR_AWAY; y[k] = v.ys[tl + L * k]; z[k] = v.zs[tl + L * k];
         qm[k] = on ? q[k] : 0.0;
         col[k] = on ? info_col(info[k]) : sys.zero_col;
     }
@@ -297,25 +351,25 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
         else stage_site_energy<SPL, 0, 0>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
     }
     // differenced per lane before the reduction (less cancellation than reducing the two ~100x larger sums)
-    const double dE = warp_sum(eE - eS);
-    if (TRACE) { eS = warp_sum(eS); eE = warp_sum(eE); }
-    if (lane == 0) {
+    const double dE = crew_team_sum<L>(eE - eS, mask);
+    if (TRACE) { eS = crew_team_sum<L>(eS, mask); eE = crew_team_sum<L>(eE, mask); }
+    if (tl == 0) {
         cs->oob = 0;
         cs->dE = dE;
         if (TRACE) { cs->eS = eS; cs->eE = eE; }
     }
 }
 
-// Space.calcEnergy (Space.java:648-658) of the chain's committed structure, whole warp.
-template <int SPL, bool HAS_EXP>
+// Space.calcEnergy (Space.java:648-658) of the chain's committed structure, one team.
+template <int L, int SPL, bool HAS_EXP>
 __device__ __forceinline__ double crew_total_energy(const unsigned char *smem, const CrewView &v, const DevSystem &sys, const int (&info)[SPL],
-                                                    const double (&q)[SPL], int lane)
+                                                    const double (&q)[SPL], int tl, unsigned mask)
 {
-    using TL = CrewTables<SPL>;
+    using TL = CrewTables<L, SPL>;
     const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
     double x[SPL], y[SPL], z[SPL];
 #pragma unroll
-    for (int k = 0; k < SPL; k++) { x[k] = v.xs[lane + 32 * k]; y[k] = v.ys[lane + 32 * k]; z[k] = v.zs[lane + 32 * k]; }
+    for (int k = 0; k < SPL; k++) { x[k] = v.xs[tl + L * k]; y[k] = v.ys[tl + L * k]; z[k] = v.zs[tl + L * k]; }
     double acc = 0.0;
     for (int p = 0; p < TL::NPOS; p++) {
         const int infi = TL::pos_info(smem, p);
@@ -333,26 +387,26 @@ __device__ __forceinline__ double crew_total_energy(const unsigned char *smem, c
             }
         }
     }
-    return warp_sum(acc);
+    return crew_team_sum<L>(acc, mask);
 }
 
-// shared SoA (position order) <-> global [S][3] (site order), whole warp
-template <int SPL>
-__device__ __forceinline__ void crew_sites_to_global(const CrewView &v, double *dst, const DevSystem &sys, int lane)
+// shared SoA (position order) <-> global [S][3] (site order), one team
+template <int L, int SPL>
+__device__ __forceinline__ void crew_sites_to_global(const CrewView &v, double *dst, const DevSystem &sys, int tl)
 {
 #pragma unroll
     for (int k = 0; k < SPL; k++) {
-        const int p = lane + 32 * k, i = sys.pos_site[p];
+        const int p = tl + L * k, i = sys.pos_site[p];
         if (i >= 0) { dst[3 * i] = v.xs[p]; dst[3 * i + 1] = v.ys[p]; dst[3 * i + 2] = v.zs[p]; }
     }
 }
 
-template <int SPL>
-__device__ __forceinline__ void crew_sites_from_global(const CrewView &v, const double *src, const DevSystem &sys, int lane)
+template <int L, int SPL>
+__device__ __forceinline__ void crew_sites_from_global(const CrewView &v, const double *src, const DevSystem &sys, int tl)
 {
 #pragma unroll
     for (int k = 0; k < SPL; k++) {
-        const int p = lane + 32 * k, i = sys.pos_site[p];
+        const int p = tl + L * k, i = sys.pos_site[p];
         v.xs[p] = i >= 0 ? src[3 * i] : FAR_AWAY;
         v.ys[p] = i >= 0 ? src[3 * i + 1] : FAR_AWAY;
         v.zs[p] = i >= 0 ? src[3 * i + 2] : FAR_AWAY;
@@ -467,11 +521,12 @@ struct CrewPick {
     bool ok;
 };
 
-template <int SPL, int LJS, bool HAS_EXP, bool TRACE, int EW, int MINB>
+template <int L, int SPL, int LJS, bool HAS_EXP, bool TRACE, int EW, int MINB>
 __global__ void __launch_bounds__(32 * (1 + EW), MINB)
 crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, const int max_mol_sites)
 {
-    using TL = CrewTables<SPL>;
+    using TL = CrewTables<L, SPL>;
+    constexpr int TPW = 32 / L;                    // chains an energy warp evaluates side by side
     constexpr int NT = 32 * (1 + EW);
     extern __shared__ __align__(16) unsigned char smem[];
     const DevSystem &sys = P.sys;
@@ -482,25 +537,32 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
     const long long chain0 = (long long)blockIdx.x * C;
     const int nloc = (int)((P.n_chains - chain0 < C) ? P.n_chains - chain0 : C);
 
-    // chain state -> shared memory (every warp takes whole chains)
-    for (int c = warp; c < nloc; c += 1 + EW) {
-        const CrewView v = crew_view<SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
-        const long long ch = chain0 + c;
-        const int *src = (const int *)(P.ctrl + ch);
-        int *dst = (int *)&v.cs->ctrl;
-        for (int i = lane; i < (int)(sizeof(ChainCtrl) / 4); i += 32) dst[i] = src[i];
-        const double *cg = P.com + (size_t)ch * sys.n_mol * 3;
-        for (int i = lane; i < sys.n_mol * 3; i += 32) v.com[i] = cg[i];
-        crew_sites_from_global<SPL>(v, P.sites + (size_t)ch * sys.n_sites * 3, sys, lane);
-        __syncwarp();
-        if (lane == 0) {
-            v.cs->sch = P.sched[v.cs->ctrl.sched];
-            v.cs->mt = P.mt + (size_t)ch * 3 * 2 * MT_N;
-            v.cs->req = REQ_IDLE; v.cs->snap_slot = -1; v.cs->commit = -1; v.cs->slot = 0; v.cs->oob = 0;
+    const int tl = lane % L;                                         // lane inside its team
+    const int team = lane / L;
+    const unsigned mask = team_mask<L, 1>();
+
+    // chain state -> shared memory (every team takes whole chains)
+    for (int c0 = warp * TPW; c0 < nloc; c0 += (1 + EW) * TPW) {
+        const int c = c0 + team;
+        if (c < nloc) {
+            const CrewView v = crew_view<L, SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
+            const long long ch = chain0 + c;
+            const int *src = (const int *)(P.ctrl + ch);
+            int *dst = (int *)&v.cs->ctrl;
+            for (int i = tl; i < (int)(sizeof(ChainCtrl) / 4); i += L) dst[i] = src[i];
+            const double *cg = P.com + (size_t)ch * sys.n_mol * 3;
+            for (int i = tl; i < sys.n_mol * 3; i += L) v.com[i] = cg[i];
+            crew_sites_from_global<L, SPL>(v, P.sites + (size_t)ch * sys.n_sites * 3, sys, tl);
+            __syncwarp(mask);
+            if (tl == 0) {
+                v.cs->sch = P.sched[v.cs->ctrl.sched];
+                v.cs->mt = P.mt + (size_t)ch * 3 * 2 * MT_N;
+                v.cs->req = REQ_IDLE; v.cs->snap_slot = -1; v.cs->commit = -1; v.cs->slot = 0; v.cs->oob = 0;
+            }
+            if (tl < 3) { v.cs->wr[tl] = 0; v.cs->rd[tl] = 0; }
+            __syncwarp(mask);
+            if (!v.cs->ctrl.done) crew_ring_fill<L>(v.cs, tl, mask);
         }
-        if (lane < 3) { v.cs->wr[lane] = 0; v.cs->rd[lane] = 0; }
-        __syncwarp();
-        if (!v.cs->ctrl.done) crew_ring_fill(v.cs, lane);
     }
     __syncthreads();
 
@@ -513,7 +575,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
     if (warp == 0) {
         // ================================================================ control warp: lane c <-> chain c
         const bool mine = lane < nloc;
-        const CrewView v = crew_view<SPL>(chains, mine ? lane : 0, stride, sys.n_mol, max_mol_sites);
+        const CrewView v = crew_view<L, SPL>(chains, mine ? lane : 0, stride, sys.n_mol, max_mol_sites);
         CrewChain *cs = v.cs;
         ChainCtrl *c = &cs->ctrl;
         const tr_schedule &sch = cs->sch;
@@ -794,33 +856,35 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             mt_cursor_rewind(c->rng[STREAM_R], cs->wr[STREAM_R] - rdR);
         }
     } else {
-        // ================================================================ energy warps: warp <-> chains
+        // ================================================================ energy warps: team <-> chains
         int info[SPL];
         double q[SPL];
 #pragma unroll
-        for (int k = 0; k < SPL; k++) { info[k] = TL::pos_info(smem, lane + 32 * k); q[k] = TL::qpos(smem, lane + 32 * k); }
+        for (int k = 0; k < SPL; k++) { info[k] = TL::pos_info(smem, tl + L * k); q[k] = TL::qpos(smem, tl + L * k); }
         for (;;) {
             crew_bar(NT);                                   // B1
             if (TL::alive(smem) == 0) break;
             TM(const long long tm0 = clock64(); tm_rounds++;)
-            for (int c = warp - 1; c < nloc; c += EW) {
-                const CrewView v = crew_view<SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
+            for (int c0 = (warp - 1) * TPW; c0 < nloc; c0 += EW * TPW) {
+                const int c = c0 + team;
+                if (c >= nloc) continue;
+                const CrewView v = crew_view<L, SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
                 const int req = v.cs->req;
                 if (req == REQ_IDLE) continue;
                 TM(const long long tm1 = clock64();)
-                const MtWindow w = crew_ring_begin(v.cs, lane);          // loads fly while the move is evaluated
+                const CrewWindow<L> w = crew_ring_begin<L>(v.cs, tl);    // loads fly while the move is evaluated
                 const int commit = v.cs->commit;
-                if (commit >= 0) crew_commit<SPL>(smem, v, v.cs->desc[commit], lane);
-                if (req == REQ_MOVE) crew_move<SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, v.cs->desc[v.cs->slot], info, q, lane);
+                if (commit >= 0) crew_commit<L, SPL>(smem, v, v.cs->desc[commit], tl, mask);
+                if (req == REQ_MOVE) crew_move<L, SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, v.cs->desc[v.cs->slot], info, q, tl, mask);
                 else if (req == REQ_TOTAL) {
-                    const double e = crew_total_energy<SPL, HAS_EXP>(smem, v, sys, info, q, lane);
-                    if (lane == 0) v.cs->etot = e;
+                    const double e = crew_total_energy<L, SPL, HAS_EXP>(smem, v, sys, info, q, tl, mask);
+                    if (tl == 0) v.cs->etot = e;
                     const int k = v.cs->snap_slot;
                     if (k >= 0)
-                        crew_sites_to_global<SPL>(v, P.snap_sites + ((size_t)(chain0 + c) * P.max_snaps + k) * (size_t)sys.n_sites * 3, sys, lane);
+                        crew_sites_to_global<L, SPL>(v, P.snap_sites + ((size_t)(chain0 + c) * P.max_snaps + k) * (size_t)sys.n_sites * 3, sys, tl);
                 }
                 TM(const long long tm2 = clock64(); tm_a += tm2 - tm1;)
-                crew_ring_end(v.cs, w, lane);
+                crew_ring_end<L>(v.cs, w, tl, mask);
                 TM(tm_b += clock64() - tm2;)
             }
             TM(tm_c += clock64() - tm0;)
@@ -831,15 +895,17 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
     __syncthreads();
 
     // chain state -> global memory
-    for (int c = warp; c < nloc; c += 1 + EW) {
-        const CrewView v = crew_view<SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
+    for (int c0 = warp * TPW; c0 < nloc; c0 += (1 + EW) * TPW) {
+        const int c = c0 + team;
+        if (c >= nloc) continue;
+        const CrewView v = crew_view<L, SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
         const long long ch = chain0 + c;
         int *dst = (int *)(P.ctrl + ch);
         const int *src = (const int *)&v.cs->ctrl;
-        for (int i = lane; i < (int)(sizeof(ChainCtrl) / 4); i += 32) dst[i] = src[i];
+        for (int i = tl; i < (int)(sizeof(ChainCtrl) / 4); i += L) dst[i] = src[i];
         double *cg = P.com + (size_t)ch * sys.n_mol * 3;
-        for (int i = lane; i < sys.n_mol * 3; i += 32) cg[i] = v.com[i];
-        crew_sites_to_global<SPL>(v, P.sites + (size_t)ch * sys.n_sites * 3, sys, lane);
+        for (int i = tl; i < sys.n_mol * 3; i += L) cg[i] = v.com[i];
+        crew_sites_to_global<L, SPL>(v, P.sites + (size_t)ch * sys.n_sites * 3, sys, tl);
     }
 #undef TM
 }

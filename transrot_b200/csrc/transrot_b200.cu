@@ -136,7 +136,6 @@ bool pick_variant(const tr_ctx *ctx, int n_sites, int tpc, Variant *out)
 {
     for (const Variant &v : kVariants) {
         if (tpc > 0 && v.tpc() != tpc) continue;
-        if (tpc == 0 && v.L != 32) continue;      // auto: the crew kernel's layout (32 lanes per chain), then a block per chain
         if (v.tpc() * v.SPL >= n_sites) { *out = v; return true; }
     }
     (void)ctx;
@@ -255,10 +254,13 @@ cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol,
 // ---- crew kernel (crew.cuh): launch geometry and dispatch ---------------------------------------
 
 #ifndef TR_CREW_EW
-#define TR_CREW_EW 4          // energy warps per block
+#define TR_CREW_EW 7          // energy warps per block
 #endif
 #ifndef TR_CREW_MINB
-#define TR_CREW_MINB 4        // blocks per SM the register budget is squeezed for
+#define TR_CREW_MINB 2        // blocks per SM the register budget is squeezed for
+#endif
+#ifndef TR_CREW_BPS
+#define TR_CREW_BPS 2         // co-resident blocks per SM the chains-per-block choice aims at
 #endif
 
 int env_int(const char *name, int dflt)
@@ -267,11 +269,11 @@ int env_int(const char *name, int dflt)
     return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int SPL>
+template <int L, int SPL>
 void crew_sizes_t(const tr_ctx *ctx, int max_mol_sites, int *tables, int *stride)
 {
-    *tables = CrewTables<SPL>::table_bytes(ctx->sys.n_types, ctx->sys.has_exp != 0);
-    *stride = CrewTables<SPL>::chain_bytes(ctx->sys.n_mol, max_mol_sites);
+    *tables = CrewTables<L, SPL>::table_bytes(ctx->sys.n_types, ctx->sys.has_exp != 0);
+    *stride = CrewTables<L, SPL>::chain_bytes(ctx->sys.n_mol, max_mol_sites);
 }
 
 int max_mol_sites_of(const tr_ctx *ctx)
@@ -281,20 +283,27 @@ int max_mol_sites_of(const tr_ctx *ctx)
     return m;
 }
 
+#define TR_CREW_CASES(CALL)                          \
+    switch (ctx->variant.L * 100 + ctx->variant.SPL) { \
+    case 1601: CALL(16, 1); break;                   \
+    case 1602: CALL(16, 2); break;                   \
+    case 1604: CALL(16, 4); break;                   \
+    case 3204: CALL(32, 4); break;                   \
+    case 3206: CALL(32, 6); break;                   \
+    default: return fail(ctx, TR_ELIMIT, "Error: no crew kernel for %d lanes x %d sites per lane", ctx->variant.L, ctx->variant.SPL); \
+    }
+
 // Chains per block C, bytes per chain region and dynamic shared memory of the crew kernel.  C is chosen so
-// that the grid fills every SM with TR_CREW_BPS (default 4) co-resident blocks in ONE wave when the chains
-// fit; with more chains than that the grid simply runs in several waves.
+// that the grid fills every SM with TR_CREW_BPS co-resident blocks in ONE wave when the chains fit; with more
+// chains than that the grid simply runs in several waves.
 int crew_geometry(tr_ctx *ctx, long long n_chains, int *C, int *stride, int *smem)
 {
     int tables = 0;
     const int maxs = max_mol_sites_of(ctx);
-    switch (ctx->variant.SPL) {
-    case 2: crew_sizes_t<2>(ctx, maxs, &tables, stride); break;
-    case 4: crew_sizes_t<4>(ctx, maxs, &tables, stride); break;
-    case 6: crew_sizes_t<6>(ctx, maxs, &tables, stride); break;
-    default: return fail(ctx, TR_ELIMIT, "Error: no crew kernel for %d sites per lane", ctx->variant.SPL);
-    }
-    const int bps = std::max(1, env_int("TR_CREW_BPS", 4));
+#define CALL_SIZES(L, SPL) crew_sizes_t<L, SPL>(ctx, maxs, &tables, stride)
+    TR_CREW_CASES(CALL_SIZES)
+#undef CALL_SIZES
+    const int bps = std::max(1, env_int("TR_CREW_BPS", TR_CREW_BPS));
     const int per_block = std::min(ctx->max_smem_optin, (ctx->smem_per_sm - 1024 * bps) / bps);
     int c_fit = (per_block - tables) / *stride;
     if (c_fit < 1) c_fit = (ctx->max_smem_optin - tables) / *stride;     // fewer co-resident blocks, but it runs
@@ -311,33 +320,33 @@ int crew_geometry(tr_ctx *ctx, long long n_chains, int *C, int *stride, int *sme
     return TR_OK;
 }
 
-template <int SPL, int LJS, bool HAS_EXP>
+template <int L, int SPL, int LJS, bool HAS_EXP>
 cudaError_t launch_crew_lj(tr_ctx *ctx, const KParams &P, int C, int stride, int smem, int maxs)
 {
     constexpr int EW = TR_CREW_EW;
     const unsigned blocks = (unsigned)((P.n_chains + C - 1) / C);
     cudaError_t e;
     if (P.trace) {
-        auto kern = crew_kernel<SPL, SPL, HAS_EXP, true, EW, 1>;        // tracing: one generic variant
+        auto kern = crew_kernel<L, SPL, SPL, HAS_EXP, true, EW, 1>;        // tracing: one generic variant
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
         kern<<<blocks, 32 * (1 + EW), smem, ctx->stream>>>(P, C, stride, maxs);
     } else {
-        auto kern = crew_kernel<SPL, LJS, HAS_EXP, false, EW, TR_CREW_MINB>;
+        auto kern = crew_kernel<L, SPL, LJS, HAS_EXP, false, EW, TR_CREW_MINB>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
         kern<<<blocks, 32 * (1 + EW), smem, ctx->stream>>>(P, C, stride, maxs);
     }
     return cudaGetLastError();
 }
 
-template <int SPL, bool HAS_EXP>
+template <int L, int SPL>
 cudaError_t launch_crew_t(tr_ctx *ctx, const KParams &P, int C, int stride, int smem, int maxs)
 {
     constexpr int THIRD = (SPL + 2) / 3 < 1 ? 1 : (SPL + 2) / 3;
-    const int lj_slots = (P.sys.n_lj_pos + 31) / 32;
-    if (HAS_EXP) return launch_crew_lj<SPL, SPL, HAS_EXP>(ctx, P, C, stride, smem, maxs);
-    if (lj_slots == 0) return launch_crew_lj<SPL, 0, HAS_EXP>(ctx, P, C, stride, smem, maxs);
-    if (lj_slots <= THIRD) return launch_crew_lj<SPL, THIRD, HAS_EXP>(ctx, P, C, stride, smem, maxs);
-    return launch_crew_lj<SPL, SPL, HAS_EXP>(ctx, P, C, stride, smem, maxs);
+    const int lj_slots = (P.sys.n_lj_pos + L - 1) / L;
+    if (P.sys.has_exp) return launch_crew_lj<L, SPL, SPL, true>(ctx, P, C, stride, smem, maxs);
+    if (lj_slots == 0) return launch_crew_lj<L, SPL, 0, false>(ctx, P, C, stride, smem, maxs);
+    if (lj_slots <= THIRD) return launch_crew_lj<L, SPL, THIRD, false>(ctx, P, C, stride, smem, maxs);
+    return launch_crew_lj<L, SPL, SPL, false>(ctx, P, C, stride, smem, maxs);
 }
 
 int launch_crew(tr_ctx *ctx, const KParams &P)
@@ -346,12 +355,9 @@ int launch_crew(tr_ctx *ctx, const KParams &P)
     if (int r = crew_geometry(ctx, P.n_chains, &C, &stride, &smem)) return r;
     const int maxs = max_mol_sites_of(ctx);
     cudaError_t e = cudaErrorInvalidValue;
-    const bool he = ctx->sys.has_exp != 0;
-    switch (ctx->variant.SPL) {
-    case 2: e = he ? launch_crew_t<2, true>(ctx, P, C, stride, smem, maxs) : launch_crew_t<2, false>(ctx, P, C, stride, smem, maxs); break;
-    case 4: e = he ? launch_crew_t<4, true>(ctx, P, C, stride, smem, maxs) : launch_crew_t<4, false>(ctx, P, C, stride, smem, maxs); break;
-    case 6: e = he ? launch_crew_t<6, true>(ctx, P, C, stride, smem, maxs) : launch_crew_t<6, false>(ctx, P, C, stride, smem, maxs); break;
-    }
+#define CALL_CREW(L, SPL) e = launch_crew_t<L, SPL>(ctx, P, C, stride, smem, maxs)
+    TR_CREW_CASES(CALL_CREW)
+#undef CALL_CREW
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: crew kernel launch failed: %s", cudaGetErrorString(e));
     return TR_OK;
 }
