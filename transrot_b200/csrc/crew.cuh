@@ -29,33 +29,64 @@
 namespace tr {
 
 enum { REQ_IDLE = 0, REQ_MOVE = 1, REQ_TOTAL = 2, REQ_SYNC = 3 };
-enum { CHAIN_ABORT_RNG = 2 };      // ChainCtrl.done: ring underflow inside a nextInt rejection loop (p < 1e-50 per move)
+enum { CHAIN_ABORT_RNG = 2 };      // ChainCtrl.done: a nextInt rejection loop outran a freshly filled ring (p < 1e-50 per move)
 
-struct __align__(16) CrewDesc {    // one posted move (Space.move / Space.rotate arguments after the draws)
+// The order word a control lane posts for its chain each round.
+constexpr int ORD_REQ = 3;               // bits 0-1: REQ_*
+constexpr int ORD_SEL = 1 << 2;          // REQ_MOVE: which of the two pre-drawn successor descriptors
+constexpr int ORD_PAR = 1 << 3;          // REQ_MOVE: which descriptor pair (they alternate between rounds)
+constexpr int ORD_COMMIT = 1 << 4;       // commit the move staged last round first (setTemps)
+constexpr int ORD_FILL = 1 << 5;         // bring every ring above 32 unread words before returning (rare)
+constexpr int ORD_REFILL_SHIFT = 6;      // bits 6-7: stream whose ring gets the next window, 3 = none
+
+constexpr int CREW_RING = 128;           // tempered words per stream kept in shared memory
+constexpr int CREW_RING_LOW = CREW_RING - 32;   // a 32-word window may be appended while at most this many are unread
+
+struct __align__(16) CrewDesc {    // one drawn move (Space.move / Space.rotate arguments after the draws)
     double va, vb, vc;             // translation vector, or (sin, cos, -) of the rotation angle
-    int m, off, sm;                // particle, its first site, its site count
-    int rot;                       // 0 = Space.move, 1 = Space.rotate
-    int axis;                      // Molecule.java:68
-    int pad_[3];
+    int m, off;                    // particle, its first site
+    int info;                      // site count | rot << 8 | (axis + 1) << 12
+    int pad_;
 };
+__device__ __forceinline__ int desc_sm(int info) { return info & 0xff; }
+__device__ __forceinline__ int desc_rot(int info) { return (info >> 8) & 1; }
+__device__ __forceinline__ int desc_axis(int info) { return ((info >> 12) & 7) - 1; }
 
 struct __align__(16) CrewChain {
     ChainCtrl ctrl;
     tr_schedule sch;
     uint32_t *mt;                  // global: [3][2][624] ping-pong blocks of this chain
-    uint32_t ring[3][MT_RING];
-    CrewDesc desc[2];              // the move posted this round and the one before it (still staged: commit source)
-    int wr[3];                     // words appended to each ring so far (energy warps)
-    int rd[3];                     // words consumed from each ring so far (control lane, published per round)
-    int req;                       // this round's request to the energy warps
-    int slot;                      // REQ_MOVE: which desc[] is the new move
-    int commit;                    // desc[] slot whose staged trial coordinates are to be committed first (setTemps), or -1
+    uint32_t ring[3][CREW_RING];
+    CrewDesc desc[2][2];           // [pair][candidate]: the control lane writes one pair while the team reads the other
+    // control lane -> team
+    int order;                     // ORD_* bits
     int snap_slot;                 // REQ_TOTAL: write(n) slot to dump the structure into, or -1
-    int oob;                       // REQ_MOVE result: rejected by the 0.75 * spaceLen box, no energy evaluated
-    int pad_;
-    double dE, eS, eE;             // REQ_MOVE results (eS, eE only when tracing)
-    double etot;                   // REQ_TOTAL result
+    int rd[3];                     // ring words consumed so far (published with ORD_FILL only)
+    int pad0_[3];
+    // team -> control lane
+    double dE;                     // REQ_MOVE: eEnd - eStart
+    int oob;                       // REQ_MOVE: rejected by the 0.75 * spaceLen box, no energy evaluated
+    int pad1_;
+    double eS, eE;                 // REQ_MOVE, tracing only
+    double etot;                   // REQ_TOTAL: Space.calcEnergy
+    double bound;                  // 0.75 * spaceLen (Space.java:663,706)
+    int wr[3];                     // ring words appended so far
+    int pad2_;
+    // team-private between rounds: what a commit of the move staged last round needs
+    int prev_p[TR_MAX_MOL_SITES];  // positions of its sites (-1 beyond s_m)
+    double prev_v[3];              // its centre-of-mass shift
+    int prev_m;                    // its particle, or -1 for a rotation (Molecule.rotateTemp leaves the centre of mass alone)
+    int pad3_;
 };
+
+#ifdef TR_CREW_TIMING
+__device__ long long g_tm[8];
+#define TMG(i, expr) do { if (blockIdx.x == 3 && threadIdx.x == 32) g_tm[i] += (expr); } while (0)
+#define TMCLK() clock64()
+#else
+#define TMG(i, expr) do { } while (0)
+#define TMCLK() 0LL
+#endif
 
 constexpr int CREW_BAR = 1;        // named barrier used by both roles
 
@@ -153,12 +184,10 @@ __device__ __forceinline__ double crew_team_sum(double a, unsigned mask)
 // ---- energy-warp services -----------------------------------------------------------------------
 
 // Ring upkeep.  The control lane reads ahead of the published `rd` cursors while the energy teams append
-// behind `wr`, so a window is only ever appended when at most 32 words are unread (64-word rings).
-// crew_ring_begin picks the neediest stream and issues the global loads of its next window; the pair
-// arithmetic of the round then hides their L2 latency; crew_ring_end twists, tempers and appends.
-// Afterwards every stream is brought to >= CREW_RING_FLOOR unread words synchronously (rare).
-// A team of L = 16 lanes takes two words of the window per lane.
-constexpr int CREW_RING_FLOOR = 24;
+// behind `wr`, so a 32-word window is only ever appended when at most CREW_RING_LOW words are unread.
+// The control lane decides which stream gets the next window (it sees both cursors) and says so in the order
+// word; crew_ring_begin issues the global loads of that window, the pair arithmetic of the round hides their L2
+// latency, crew_ring_end twists, tempers and appends.  A team of L = 16 lanes takes two words per lane.
 
 template <int L>
 struct CrewWindow {
@@ -167,14 +196,10 @@ struct CrewWindow {
 };
 
 template <int L>
-__device__ __forceinline__ CrewWindow<L> crew_ring_begin(CrewChain *cs, int tl)
+__device__ __forceinline__ CrewWindow<L> crew_ring_begin(CrewChain *cs, int s, int tl)
 {
     CrewWindow<L> w;
-    const int aM = cs->wr[0] - cs->rd[0], aS = cs->wr[1] - cs->rd[1], aR = cs->wr[2] - cs->rd[2];
-    int s = 0, amin = aM;
-    if (aS < amin) { amin = aS; s = 1; }
-    if (aR < amin) { amin = aR; s = 2; }
-    w.s = amin > 32 ? -1 : s;
+    w.s = s > 2 ? -1 : s;
     w.par = w.gen = w.fed = w.count = w.load = w.wr = 0;
 #pragma unroll
     for (int j = 0; j < 32 / L; j++) w.a[j] = w.b[j] = w.far[j] = 0u;
@@ -207,79 +232,45 @@ __device__ __forceinline__ CrewWindow<L> crew_ring_begin(CrewChain *cs, int tl)
 template <int L>
 __device__ __forceinline__ void crew_ring_end(CrewChain *cs, const CrewWindow<L> &w, int tl, unsigned mask)
 {
-    if (w.s >= 0) {
-        uint32_t *mt = cs->mt + w.s * 2 * MT_N;
+    if (w.s < 0) return;
+    uint32_t *mt = cs->mt + w.s * 2 * MT_N;
 #pragma unroll
-        for (int j = 0; j < 32 / L; j++) {
-            const int i = tl + j * L;
-            if (i < w.count) {
-                uint32_t v = w.a[j];
-                if (!w.load) {
-                    const uint32_t y = (w.a[j] & 0x80000000u) | (w.b[j] & 0x7fffffffu);
-                    v = w.far[j] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-                    mt[w.par * MT_N + w.fed + i] = v;
-                }
-                cs->ring[w.s][(w.wr + i) & (MT_RING - 1)] = mt_temper(v);
+    for (int j = 0; j < 32 / L; j++) {
+        const int i = tl + j * L;
+        if (i < w.count) {
+            uint32_t v = w.a[j];
+            if (!w.load) {
+                const uint32_t y = (w.a[j] & 0x80000000u) | (w.b[j] & 0x7fffffffu);
+                v = w.far[j] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                mt[w.par * MT_N + w.fed + i] = v;
             }
-        }
-        if (tl == 0) {
-            MtCursor c;
-            c.par = w.par; c.gen = w.load ? w.gen : w.fed + w.count; c.fed = w.fed + w.count;
-            cs->ctrl.rng[w.s] = c;
-            cs->wr[w.s] = w.wr + w.count;
-        }
-        __syncwarp(mask);
-    }
-    const int aM = cs->wr[0] - cs->rd[0], aS = cs->wr[1] - cs->rd[1], aR = cs->wr[2] - cs->rd[2];
-    if (aM < CREW_RING_FLOOR || aS < CREW_RING_FLOOR || aR < CREW_RING_FLOOR) {
-        for (int s = 0; s < 3; s++) {
-            int wr = cs->wr[s], have = wr - cs->rd[s];
-            if (have >= CREW_RING_FLOOR) continue;
-            do {
-                const int n = mt_ring_refill_words<L>(cs->mt + s * 2 * MT_N, cs->ring[s], &cs->ctrl.rng[s], wr, tl, mask);
-                wr += n; have += n;
-            } while (have <= 32);
-            if (tl == 0) cs->wr[s] = wr;
-            __syncwarp(mask);
+            cs->ring[w.s][(w.wr + i) & (CREW_RING - 1)] = mt_temper(v);
         }
     }
-}
-
-// Blocking fill to more than 32 unread words per stream (kernel prologue).
-template <int L>
-__device__ __forceinline__ void crew_ring_fill(CrewChain *cs, int tl, unsigned mask)
-{
-    for (int s = 0; s < 3; s++) {
-        int wr = cs->wr[s], have = wr - cs->rd[s];
-        while (have <= 32) {
-            const int n = mt_ring_refill_words<L>(cs->mt + s * 2 * MT_N, cs->ring[s], &cs->ctrl.rng[s], wr, tl, mask);
-            wr += n; have += n;
-        }
-        if (tl == 0) cs->wr[s] = wr;
-        __syncwarp(mask);
-    }
-}
-
-// setTemps (Molecule.java:128-135) of the move staged in the previous round: its trial coordinates are still in
-// the staging area.  Lanes a < s_m take one site each; lane 0 moves the tracked centre of mass of a translation.
-template <int L, int SPL>
-__device__ __forceinline__ void crew_commit(const unsigned char *smem, const CrewView &v, const CrewDesc &d, int tl, unsigned mask)
-{
-    if (tl < d.sm) {
-        const int p = CrewTables<L, SPL>::site_pos(smem, d.off + tl);
-        const StageSite *st = &v.stage[tl];
-        v.xs[p] = st->nx; v.ys[p] = st->ny; v.zs[p] = st->nz;
-    }
-    if (tl == 0 && !d.rot) {          // m.x = m.tempx
-        v.com[3 * d.m] = __dadd_rn(v.com[3 * d.m], d.va);
-        v.com[3 * d.m + 1] = __dadd_rn(v.com[3 * d.m + 1], d.vb);
-        v.com[3 * d.m + 2] = __dadd_rn(v.com[3 * d.m + 2], d.vc);
+    if (tl == 0) {
+        MtCursor c;
+        c.par = w.par; c.gen = w.load ? w.gen : w.fed + w.count; c.fed = w.fed + w.count;
+        cs->ctrl.rng[w.s] = c;
+        cs->wr[w.s] = w.wr + w.count;
     }
     __syncwarp(mask);
 }
 
+// Blocking fill of every ring to more than CREW_RING_LOW unread words (kernel prologue; ORD_FILL).
+template <int L>
+__device__ __forceinline__ void crew_ring_fill(CrewChain *cs, int tl, unsigned mask)
+{
+    for (int s = 0; s < 3; s++) {
+        while (cs->wr[s] - cs->rd[s] <= CREW_RING_LOW) {
+            const CrewWindow<L> w = crew_ring_begin<L>(cs, s, tl);
+            crew_ring_end<L>(cs, w, tl, mask);
+        }
+    }
+}
+
 // One posted move for one chain, one team: trial geometry of the s_m sites (lane a < s_m <-> site a) into the
 // staging area with the 0.75 * spaceLen box test (Space.java:663,706), then eEnd - eStart (Space.java:711-718).
+// Also leaves what a later commit needs (prev_p, prev_m, prev_v).
 template <int L, int SPL, int LJS, bool HAS_EXP, bool TRACE>
 __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewView &v, const DevSystem &sys, const CrewDesc &d,
                                           const int (&info)[SPL], const double (&q)[SPL], int tl, unsigned mask)
@@ -287,53 +278,9 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
     using TL = CrewTables<L, SPL>;
     static_assert(TR_MAX_MOL_SITES <= L, "one lane per site of the moved particle");
     CrewChain *cs = v.cs;
-    const int m = d.m, sm = d.sm;
-    bool oob = false;
-    if (tl < sm) {
-        const int p = TL::site_pos(smem, d.off + tl);
-        const int inf = TL::pos_info(smem, p);
-        double ox = v.xs[p], oy = v.ys[p], oz = v.zs[p], tx, ty, tz;
-        if (d.rot) {
-            // Molecule.java:70-95, operation for operation, no contraction (va = sin, vb = cos)
-            const double cx = v.com[3 * m], cy = v.com[3 * m + 1], cz = v.com[3 * m + 2];
-            const double va = d.va, vb = d.vb, nsn = __dmul_rn(-1.0, d.va);
-            const double ax = __dsub_rn(ox, cx), ay = __dsub_rn(oy, cy), az = __dsub_rn(oz, cz);
-            if (d.axis == 0) {
-                tx = ax;
-                ty = __dadd_rn(__dmul_rn(vb, ay), __dmul_rn(va, az));
-                tz = __dadd_rn(__dmul_rn(nsn, ay), __dmul_rn(vb, az));
-            } else if (d.axis == 1) {
-                tx = __dsub_rn(__dmul_rn(vb, ax), __dmul_rn(va, az));
-                ty = ay;
-                tz = __dadd_rn(__dmul_rn(va, ax), __dmul_rn(vb, az));
-            } else {
-                tx = __dadd_rn(__dmul_rn(vb, ax), __dmul_rn(va, ay));
-                ty = __dadd_rn(__dmul_rn(nsn, ax), __dmul_rn(vb, ay));
-                tz = az;
-            }
-            // a.x += x: the committed coordinate keeps the (a.x - x) + x round trip even if the move is rejected
-            ox = __dadd_rn(ax, cx); oy = __dadd_rn(ay, cy); oz = __dadd_rn(az, cz);
-            v.xs[p] = ox; v.ys[p] = oy; v.zs[p] = oz;
-            tx = __dadd_rn(tx, cx); ty = __dadd_rn(ty, cy); tz = __dadd_rn(tz, cz);
-        } else {
-            tx = __dadd_rn(ox, d.va); ty = __dadd_rn(oy, d.vb); tz = __dadd_rn(oz, d.vc);
-        }
-        StageSite st;
-        st.ox = ox; st.oy = oy; st.oz = oz;
-        st.nx = tx; st.ny = ty; st.nz = tz;
-        st.kq = __dmul_rn(K_VALUE, TL::qpos(smem, p));
-        st.row = info_type(inf) * sys.row_stride; st.lj = info_lj(inf);
-        v.stage[tl] = st;
-        const double b = cs->ctrl.space_len * 0.75;      // t > L*0.75 || t < L*-0.75; the lower bound is the exact negative
-        oob = (fabs(tx) > b) | (fabs(ty) > b) | (fabs(tz) > b);
-    }
-    const bool any_oob = (__ballot_sync(mask, oob) & mask) != 0u;
-    __syncwarp(mask);                                       // staging stores before the broadcast reads below
-    if (any_oob) {
-        if (tl == 0) cs->oob = 1;
-        return;
-    }
-    const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
+    const int m = d.m, sm = desc_sm(d.info), rot = desc_rot(d.info), axis = desc_axis(d.info);
+    const long long tq0 = TMCLK();
+    // this lane's positions; those of m itself are taken out by a far-away x, a zero charge and the all-zero table column
     double x[SPL], y[SPL], z[SPL], qm[SPL];
     int col[SPL];
 #pragma unroll
@@ -343,6 +290,62 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
         qm[k] = on ? q[k] : 0.0;
         col[k] = on ? info_col(info[k]) : sys.zero_col;
     }
+    bool oob = false;
+    if (tl < TR_MAX_MOL_SITES) {
+        int p = -1;
+        if (tl < sm) {
+            p = TL::site_pos(smem, d.off + tl);
+            const int inf = TL::pos_info(smem, p);
+            double ox = v.xs[p], oy = v.ys[p], oz = v.zs[p], tx, ty, tz;
+            if (rot) {
+                // Molecule.java:70-95, operation for operation, no contraction (va = sin, vb = cos)
+                const double cx = v.com[3 * m], cy = v.com[3 * m + 1], cz = v.com[3 * m + 2];
+                const double va = d.va, vb = d.vb, nsn = __dmul_rn(-1.0, d.va);
+                const double ax = __dsub_rn(ox, cx), ay = __dsub_rn(oy, cy), az = __dsub_rn(oz, cz);
+                if (axis == 0) {
+                    tx = ax;
+                    ty = __dadd_rn(__dmul_rn(vb, ay), __dmul_rn(va, az));
+                    tz = __dadd_rn(__dmul_rn(nsn, ay), __dmul_rn(vb, az));
+                } else if (axis == 1) {
+                    tx = __dsub_rn(__dmul_rn(vb, ax), __dmul_rn(va, az));
+                    ty = ay;
+                    tz = __dadd_rn(__dmul_rn(va, ax), __dmul_rn(vb, az));
+                } else {
+                    tx = __dadd_rn(__dmul_rn(vb, ax), __dmul_rn(va, ay));
+                    ty = __dadd_rn(__dmul_rn(nsn, ax), __dmul_rn(vb, ay));
+                    tz = az;
+                }
+                // a.x += x: the committed coordinate keeps the (a.x - x) + x round trip even if the move is rejected
+                ox = __dadd_rn(ax, cx); oy = __dadd_rn(ay, cy); oz = __dadd_rn(az, cz);
+                v.xs[p] = ox; v.ys[p] = oy; v.zs[p] = oz;
+                tx = __dadd_rn(tx, cx); ty = __dadd_rn(ty, cy); tz = __dadd_rn(tz, cz);
+            } else {
+                tx = __dadd_rn(ox, d.va); ty = __dadd_rn(oy, d.vb); tz = __dadd_rn(oz, d.vc);
+            }
+            StageSite st;
+            st.ox = ox; st.oy = oy; st.oz = oz;
+            st.nx = tx; st.ny = ty; st.nz = tz;
+            st.kq = __dmul_rn(K_VALUE, TL::qpos(smem, p));
+            st.row = info_type(inf) * sys.row_stride; st.lj = info_lj(inf);
+            v.stage[tl] = st;
+            const double b = cs->bound;                  // t > L*0.75 || t < L*-0.75; the lower bound is the exact negative
+            oob = (fabs(tx) > b) | (fabs(ty) > b) | (fabs(tz) > b);
+        }
+        cs->prev_p[tl] = p;
+        if (tl == 0) {
+            cs->prev_m = rot ? -1 : m;
+            cs->prev_v[0] = d.va; cs->prev_v[1] = d.vb; cs->prev_v[2] = d.vc;
+        }
+    }
+    const bool any_oob = (__ballot_sync(mask, oob) & mask) != 0u;
+    __syncwarp(mask);                                       // staging stores before the broadcast reads below
+    const long long tq1 = TMCLK();
+    TMG(0, tq1 - tq0);
+    if (any_oob) {
+        if (tl == 0) cs->oob = 1;
+        return;
+    }
+    const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
     double eS = 0.0, eE = 0.0;
     for (int a = 0; a < sm; a++) {
         const StageSite st = v.stage[a];
@@ -350,6 +353,8 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
         else if (LJS > 0 && st.lj) stage_site_energy<SPL, LJS, 1>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
         else stage_site_energy<SPL, 0, 0>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
     }
+    const long long tq2 = TMCLK();
+    TMG(1, tq2 - tq1);
     // differenced per lane before the reduction (less cancellation than reducing the two ~100x larger sums)
     const double dE = crew_team_sum<L>(eE - eS, mask);
     if (TRACE) { eS = crew_team_sum<L>(eS, mask); eE = crew_team_sum<L>(eE, mask); }
@@ -358,6 +363,7 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
         cs->dE = dE;
         if (TRACE) { cs->eS = eS; cs->eE = eE; }
     }
+    TMG(2, TMCLK() - tq2);
 }
 
 // Space.calcEnergy (Space.java:648-658) of the chain's committed structure, one team.
@@ -534,9 +540,8 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
     unsigned char *chains = smem + TL::table_bytes(sys.n_types, sys.has_exp);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long chain0 = (long long)blockIdx.x * C;
+    const long long chain0 = (long long)blockIdx.x * C;            // C <= EW * TPW: every chain has its own team
     const int nloc = (int)((P.n_chains - chain0 < C) ? P.n_chains - chain0 : C);
-
     const int tl = lane % L;                                         // lane inside its team
     const int team = lane / L;
     const unsigned mask = team_mask<L, 1>();
@@ -557,9 +562,11 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             if (tl == 0) {
                 v.cs->sch = P.sched[v.cs->ctrl.sched];
                 v.cs->mt = P.mt + (size_t)ch * 3 * 2 * MT_N;
-                v.cs->req = REQ_IDLE; v.cs->snap_slot = -1; v.cs->commit = -1; v.cs->slot = 0; v.cs->oob = 0;
+                v.cs->order = REQ_IDLE; v.cs->snap_slot = -1; v.cs->oob = 0; v.cs->prev_m = -1;
+                v.cs->bound = v.cs->ctrl.space_len * 0.75;
             }
             if (tl < 3) { v.cs->wr[tl] = 0; v.cs->rd[tl] = 0; }
+            if (tl < TR_MAX_MOL_SITES) v.cs->prev_p[tl] = -1;
             __syncwarp(mask);
             if (!v.cs->ctrl.done) crew_ring_fill<L>(v.cs, tl, mask);
         }
@@ -595,9 +602,11 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
         bool live = mine && !c->done;
         bool hot = false;
         // pipeline state
-        bool inflight = false, pend_total = false, total_for_init = false, bk_pending = false;
-        int commit_pending = 0, last_slot = 0;
+        bool inflight = false, pend_total = false, total_for_init = false, bk_pending = false, sel_pending = false, filled = false;
+        int commit_pending = 0, np = 0;                          // np: descriptor pair the next move is posted from
+        int refill_next = 3, refill_posted = 3;                  // stream the next order asks a window for / the one in flight
         int cur_info = 0;                                        // move in flight: m | sm << 16 | rot << 21 | magwalk << 22 | (axis + 1) << 23
+        int sel = 0;                                             // candidate chosen by the last fast post
         bool metro_ok = false, cand_ok = false;
         double rnd = 0.0, thr = 0.0, grd = 0.0;                  // Metropolis draw of the move in flight and its dE threshold
         CrewCommon cm; cm.sn = cm.cs = 0.0; cm.kindbit = cm.magw_rot = cm.magw_trans = 0; cm.axis = -1; cm.nR = 0; cm.ok = false;
@@ -652,9 +661,9 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             if (seg_moves >= (1 << 20)) flush_hot();
             bk_pending = false;
         };
-        auto ringM = [&](int pos) { return cs->ring[STREAM_M][pos & (MT_RING - 1)]; };
-        auto ringS = [&](int pos) { return cs->ring[STREAM_S][pos & (MT_RING - 1)]; };
-        auto ringR = [&](int pos) { return cs->ring[STREAM_R][pos & (MT_RING - 1)]; };
+        auto ringM = [&](int pos) { return cs->ring[STREAM_M][pos & (CREW_RING - 1)]; };
+        auto ringS = [&](int pos) { return cs->ring[STREAM_S][pos & (CREW_RING - 1)]; };
+        auto ringR = [&](int pos) { return cs->ring[STREAM_R][pos & (CREW_RING - 1)]; };
         // Main.java:199-213 + Molecule.java:67-68 at the current M / R positions (nothing is consumed here)
         auto draw_common = [&]() {
             cm.ok = false; cm.nR = 0; cm.axis = -1;
@@ -717,30 +726,40 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             k.nS = p - pos;
             k.ok = true;
         };
-        // Hand a drawn move to the energy warps; the stream cursors move past its words.
-        auto post_move = [&](const CrewPick &k) {
-            last_slot ^= 1;
+        // The descriptor the energy team reads for a drawn move.
+        auto write_desc = [&](const CrewPick &k, int pair, int which) {
             CrewDesc d;
-            d.m = k.m; d.off = k.off; d.sm = k.sm; d.rot = k.rot; d.axis = k.rot ? cm.axis : -1;
+            const int axis = k.rot ? cm.axis : -1;
             d.va = k.rot ? cm.sn : k.va; d.vb = k.rot ? cm.cs : k.vb; d.vc = k.rot ? 0.0 : k.vc;
-            d.pad_[0] = d.pad_[1] = d.pad_[2] = 0;
-            cs->desc[last_slot] = d;
-            cs->slot = last_slot;
-            cs->commit = commit_pending ? (last_slot ^ 1) : -1;
-            commit_pending = 0;
+            d.m = k.m; d.off = k.off; d.info = k.sm | (k.rot << 8) | ((axis + 1) << 12); d.pad_ = 0;
+            cs->desc[pair][which] = d;
+        };
+        // The stream cursors move past a posted move's words; remember what bookkeeping and the trace need of it.
+        auto adopt = [&](const CrewPick &k) {
             const int magwalk = k.rot ? cm.magw_rot : cm.magw_trans;
-            cur_info = k.m | (k.sm << 16) | (k.rot << 21) | (magwalk << 22) | ((d.axis + 1) << 23);
+            const int axis = k.rot ? cm.axis : -1;
+            cur_info = k.m | (k.sm << 16) | (k.rot << 21) | (magwalk << 22) | ((axis + 1) << 23);
             rdS += k.nS; rdM += 4; rdR += k.rot ? cm.nR : 0;
-            inflight = true; budget--;
+        };
+        // Which ring gets the next window: the one with the fewest unread words if that is <= 32, never the one whose
+        // window is in flight (its cursor is not final yet); 3 = none.
+        auto choose_refill = [&]() {
+            int aM = wrM - rdM, aS = wrS - rdS, aR = wrR - rdR;
+            if (refill_posted == STREAM_M) aM = CREW_RING;
+            if (refill_posted == STREAM_S) aS = CREW_RING;
+            if (refill_posted == STREAM_R) aR = CREW_RING;
+            int s = STREAM_M, amin = aM;
+            if (aS < amin) { amin = aS; s = STREAM_S; }
+            if (aR < amin) { amin = aR; s = STREAM_R; }
+            refill_next = amin <= CREW_RING_LOW ? s : 3;
         };
         if (live) load_hot();
 
         for (;;) {
             TM(const long long tm0 = clock64();)
-            // ------------------------------------------------ phase 1 (critical): results of the round that just ended
-            int req = REQ_IDLE;
+            // ------------------------------------------------ phase 1 (critical): the result of the round that just ended
+            int order = REQ_IDLE;
             if (live) {
-                wrM = cs->wr[STREAM_M]; wrS = cs->wr[STREAM_S]; wrR = cs->wr[STREAM_R];     // stable: the producers are parked
                 if (inflight) {
                     // Metropolis: Space.java:668-689 / :711-733
                     const int oob = cs->oob;
@@ -764,12 +783,17 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     if (acc) commit_pending = 1;
                     rdS += 2 * drew;
                     if (cand_ok) {
-                        post_move(drew ? cB : cA);                      // successor drawn ahead of time
-                        req = REQ_MOVE;
+                        // the successor was drawn ahead of time: post it now, settle the rest in the shadow of the energy phase
+                        sel = drew;
+                        order = REQ_MOVE | (sel ? ORD_SEL : 0) | (np ? ORD_PAR : 0) | (commit_pending ? ORD_COMMIT : 0) |
+                                (refill_next << ORD_REFILL_SHIFT);
+                        commit_pending = 0; np ^= 1;
+                        refill_posted = refill_next; refill_next = 3;
+                        sel_pending = true; inflight = true; budget--;
                     }
                     cand_ok = false;
                 }
-                if (req == REQ_IDLE) {
+                if (order == REQ_IDLE) {
                     // -------------------------------------------- phase 2 (rare): everything that is not "next move of the same point"
                     if (bk_pending) bookkeep();
                     if (pend_total) {
@@ -789,6 +813,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                         }
                         load_hot();
                     }
+                    int req = REQ_IDLE;
                     if (!c->done && !c->started) {
                         req = REQ_TOTAL; pend_total = true; total_for_init = true;
                         cs->snap_slot = (P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
@@ -801,29 +826,44 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                             load_hot();
                         }
                     }
+                    bool fill = false;
                     if (!c->done && req == REQ_IDLE && budget > 0) {
+                        wrM = cs->wr[STREAM_M]; wrS = cs->wr[STREAM_S]; wrR = cs->wr[STREAM_R];
                         draw_common();
                         if (cm.ok) draw_pick(cA, rdS);
-                        if (cm.ok && cA.ok) { post_move(cA); req = REQ_MOVE; }
-                        else c->done = CHAIN_ABORT_RNG;         // a nextInt rejection loop ran past 24 ring words
+                        if (cm.ok && cA.ok) {
+                            write_desc(cA, np, 0);
+                            adopt(cA);
+                            req = REQ_MOVE | (np ? ORD_PAR : 0);
+                            np ^= 1; inflight = true; budget--; filled = false;
+                        } else if (!filled) { fill = true; filled = true; }     // the rings ran low: one blocking fill, then retry
+                        else c->done = CHAIN_ABORT_RNG;
                     }
-                    if (req == REQ_IDLE && commit_pending) req = REQ_SYNC;      // parked with an accepted move not yet committed
-                    if (req == REQ_TOTAL || req == REQ_SYNC) {
-                        cs->commit = commit_pending ? last_slot : -1;
+                    if (fill || (req == REQ_IDLE && commit_pending)) req = REQ_SYNC;      // (parked with an accepted move not yet committed)
+                    if (req != REQ_IDLE) {
+                        order = req | (commit_pending ? ORD_COMMIT : 0) | (fill ? ORD_FILL : 0) | ((fill ? 3 : refill_next) << ORD_REFILL_SHIFT);
                         commit_pending = 0;
+                        refill_posted = fill ? 3 : refill_next; refill_next = 3;
+                        if (fill) { cs->rd[STREAM_M] = rdM; cs->rd[STREAM_S] = rdS; cs->rd[STREAM_R] = rdR; }
                     }
-                    if (c->done && req == REQ_IDLE) live = false;
+                    if (c->done && order == REQ_IDLE) live = false;
                 }
-                cs->rd[STREAM_M] = rdM; cs->rd[STREAM_S] = rdS; cs->rd[STREAM_R] = rdR;
-                cs->req = req;
-            } else if (mine) cs->req = REQ_IDLE;
-            const unsigned any = __ballot_sync(0xffffffffu, req != REQ_IDLE);
+                cs->order = order;
+                wrM = cs->wr[STREAM_M]; wrS = cs->wr[STREAM_S]; wrR = cs->wr[STREAM_R];     // stable: the producers are parked
+            } else if (mine) cs->order = REQ_IDLE;
+            const unsigned any = __ballot_sync(0xffffffffu, order != REQ_IDLE);
             if (lane == 0) TL::alive(smem) = (int)any;
             TM(const long long tm1 = clock64(); tm_a += tm1 - tm0; tm_rounds++;)
-            crew_bar(NT);                                   // B1: requests posted
+            crew_bar(NT);                                   // B1: orders posted
             if (!any) break;
             // ------------------------------------------------ phase 3: in the shadow of the energy phase
             if (live) {
+                if (sel_pending) {
+                    CrewPick k = cA;
+                    if (sel) k = cB;
+                    adopt(k);
+                    sel_pending = false;
+                }
                 if (bk_pending) bookkeep();
                 if (inflight) {
                     // the Metropolis double the move in flight will draw if dE > 0, and its threshold on dE
@@ -840,7 +880,9 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                         draw_common();
                         if (cm.ok) { draw_pick(cA, rdS); draw_pick(cB, rdS + 2); }
                         cand_ok = cm.ok && cA.ok && cB.ok;
+                        if (cand_ok) { write_desc(cA, np, 0); write_desc(cB, np, 1); }
                     }
+                    choose_refill();
                 }
             }
             TM(const long long tm2 = clock64(); tm_b += tm2 - tm1;)
@@ -856,7 +898,11 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             mt_cursor_rewind(c->rng[STREAM_R], cs->wr[STREAM_R] - rdR);
         }
     } else {
-        // ================================================================ energy warps: team <-> chains
+        // ================================================================ energy warps: one team <-> one chain
+        const int c = (warp - 1) * TPW + team;
+        const bool has = c < nloc;
+        const CrewView v = crew_view<L, SPL>(chains, has ? c : 0, stride, sys.n_mol, max_mol_sites);
+        CrewChain *cs = v.cs;
         int info[SPL];
         double q[SPL];
 #pragma unroll
@@ -865,31 +911,55 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             crew_bar(NT);                                   // B1
             if (TL::alive(smem) == 0) break;
             TM(const long long tm0 = clock64(); tm_rounds++;)
-            for (int c0 = (warp - 1) * TPW; c0 < nloc; c0 += EW * TPW) {
-                const int c = c0 + team;
-                if (c >= nloc) continue;
-                const CrewView v = crew_view<L, SPL>(chains, c, stride, sys.n_mol, max_mol_sites);
-                const int req = v.cs->req;
-                if (req == REQ_IDLE) continue;
-                TM(const long long tm1 = clock64();)
-                const CrewWindow<L> w = crew_ring_begin<L>(v.cs, tl);    // loads fly while the move is evaluated
-                const int commit = v.cs->commit;
-                if (commit >= 0) crew_commit<L, SPL>(smem, v, v.cs->desc[commit], tl, mask);
-                if (req == REQ_MOVE) crew_move<L, SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, v.cs->desc[v.cs->slot], info, q, tl, mask);
-                else if (req == REQ_TOTAL) {
-                    const double e = crew_total_energy<L, SPL, HAS_EXP>(smem, v, sys, info, q, tl, mask);
-                    if (tl == 0) v.cs->etot = e;
-                    const int k = v.cs->snap_slot;
-                    if (k >= 0)
-                        crew_sites_to_global<L, SPL>(v, P.snap_sites + ((size_t)(chain0 + c) * P.max_snaps + k) * (size_t)sys.n_sites * 3, sys, tl);
+            if (has) {
+                const int order = cs->order;
+                // what a commit needs sits at fixed addresses: these loads do not wait for the order word
+                int pp = -1;
+                double cnx = 0.0, cny = 0.0, cnz = 0.0;
+                if (tl < TR_MAX_MOL_SITES) {
+                    pp = cs->prev_p[tl];
+                    const StageSite *st = &v.stage[tl < max_mol_sites ? tl : 0];
+                    cnx = st->nx; cny = st->ny; cnz = st->nz;
                 }
-                TM(const long long tm2 = clock64(); tm_a += tm2 - tm1;)
-                crew_ring_end<L>(v.cs, w, tl, mask);
-                TM(tm_b += clock64() - tm2;)
+                const int req = order & ORD_REQ;
+                if (req != REQ_IDLE) {
+                    TM(const long long tm1 = clock64();)
+                    const CrewWindow<L> w = crew_ring_begin<L>(cs, (order >> ORD_REFILL_SHIFT) & 3, tl);    // loads fly while the move is evaluated
+                    TMG(3, TMCLK() - tm1);
+                    if (order & ORD_COMMIT) {
+                        // setTemps (Molecule.java:128-135) of the move staged last round
+                        if (pp >= 0) { v.xs[pp] = cnx; v.ys[pp] = cny; v.zs[pp] = cnz; }
+                        if (tl == 0) {
+                            const int pm = cs->prev_m;
+                            if (pm >= 0) {                  // m.x = m.tempx
+                                v.com[3 * pm] = __dadd_rn(v.com[3 * pm], cs->prev_v[0]);
+                                v.com[3 * pm + 1] = __dadd_rn(v.com[3 * pm + 1], cs->prev_v[1]);
+                                v.com[3 * pm + 2] = __dadd_rn(v.com[3 * pm + 2], cs->prev_v[2]);
+                            }
+                        }
+                        __syncwarp(mask);
+                    }
+                    TMG(4, TMCLK() - tm1);
+                    if (req == REQ_MOVE) {
+                        const CrewDesc d = cs->desc[(order & ORD_PAR) ? 1 : 0][(order & ORD_SEL) ? 1 : 0];
+                        crew_move<L, SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, d, info, q, tl, mask);
+                    } else if (req == REQ_TOTAL) {
+                        const double e = crew_total_energy<L, SPL, HAS_EXP>(smem, v, sys, info, q, tl, mask);
+                        if (tl == 0) cs->etot = e;
+                        const int k = cs->snap_slot;
+                        if (k >= 0)
+                            crew_sites_to_global<L, SPL>(v, P.snap_sites + ((size_t)(chain0 + c) * P.max_snaps + k) * (size_t)sys.n_sites * 3, sys, tl);
+                    }
+                    TM(const long long tm2 = clock64(); tm_a += tm2 - tm1;)
+                    crew_ring_end<L>(cs, w, tl, mask);
+                    if (order & ORD_FILL) crew_ring_fill<L>(cs, tl, mask);
+                    TM(tm_b += clock64() - tm2;)
+                }
             }
             TM(tm_c += clock64() - tm0;)
             crew_bar(NT);                                   // B2
         }
+        TM(if (blockIdx.x == 3 && threadIdx.x == 32) printf("block 3 warp 1 per round: geometry %lld pair %lld reduce %lld ring_begin %lld (begin+commit %lld)\n", g_tm[0] / tm_rounds, g_tm[1] / tm_rounds, g_tm[2] / tm_rounds, g_tm[3] / tm_rounds, g_tm[4] / tm_rounds);)
         TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 warp %d: rounds %lld busy %lld (work %lld ring_end %lld) cycles/round\n", warp, tm_rounds, tm_c / tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds);)
     }
     __syncthreads();

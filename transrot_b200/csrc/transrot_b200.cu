@@ -315,6 +315,7 @@ int crew_geometry(tr_ctx *ctx, long long n_chains, int *C, int *stride, int *sme
     c = std::max(1, std::min(c, c_fit));
     const int forced = ctx->crew_chains > 0 ? ctx->crew_chains : env_int("TR_CREW_C", 0);
     if (forced > 0) c = std::max(1, std::min(std::min(forced, 32), (ctx->max_smem_optin - tables) / *stride));
+    c = std::min(c, TR_CREW_EW * (32 / ctx->variant.L));          // every chain of a block has its own energy team
     *C = c;
     *smem = tables + c * *stride;
     return TR_OK;
