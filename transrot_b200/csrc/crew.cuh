@@ -31,13 +31,11 @@ namespace tr {
 enum { REQ_IDLE = 0, REQ_MOVE = 1, REQ_TOTAL = 2, REQ_SYNC = 3 };
 enum { CHAIN_ABORT_RNG = 2 };      // ChainCtrl.done: a nextInt rejection loop outran a freshly filled ring (p < 1e-50 per move)
 
-// The order word a control lane posts for its chain each round.
-constexpr int ORD_REQ = 3;               // bits 0-1: REQ_*
-constexpr int ORD_SEL = 1 << 2;          // REQ_MOVE: which of the two pre-drawn successor descriptors
-constexpr int ORD_PAR = 1 << 3;          // REQ_MOVE: which descriptor pair (they alternate between rounds)
-constexpr int ORD_COMMIT = 1 << 4;       // commit the move staged last round first (setTemps)
-constexpr int ORD_FILL = 1 << 5;         // bring every ring above 32 unread words before returning (rare)
-constexpr int ORD_REFILL_SHIFT = 6;      // bits 6-7: stream whose ring gets the next window, 3 = none
+// What a control lane posts for its chain for the NEXT round.
+enum { PLAN_IDLE = 0, PLAN_AUTO = 1, PLAN_MOVE = 2, PLAN_TOTAL = 3, PLAN_SYNC = 4 };
+constexpr int PF_COMMIT = 1;             // explicit modes: commit the move staged before (setTemps) first
+constexpr int PF_FILL = 2;               // bring every ring above CREW_RING_LOW unread words before returning (rare)
+constexpr int PF_TZERO = 4;              // PLAN_AUTO: the temperature is exactly 0 (every uphill move is rejected)
 
 constexpr int CREW_RING = 128;           // tempered words per stream kept in shared memory
 constexpr int CREW_RING_LOW = CREW_RING - 32;   // a 32-word window may be appended while at most this many are unread
@@ -52,32 +50,64 @@ __device__ __forceinline__ int desc_sm(int info) { return info & 0xff; }
 __device__ __forceinline__ int desc_rot(int info) { return (info >> 8) & 1; }
 __device__ __forceinline__ int desc_axis(int info) { return ((info >> 12) & 7) - 1; }
 
+// PLAN_AUTO: the team first settles the move it evaluated last round (Metropolis test with the pre-drawn double and
+// its dE threshold, commit if accepted), then evaluates cand[drew] - the successor for "no Metropolis double was
+// drawn" / "one was drawn".  PLAN_MOVE: evaluate cand[0].  Two plans alternate: the control lane writes one while the
+// team reads the other.
+struct __align__(16) CrewPlan {
+    CrewDesc cand[2];
+    double rnd, thr, grd, kBt;     // Space.r.nextDouble() of the Metropolis test, -kT log(rnd), its guard band, kB * T
+    int mode;                      // PLAN_*
+    int flags;                     // PF_*
+    int refill;                    // stream whose ring gets the next window, 3 = none
+    int snap_slot;                 // PLAN_TOTAL: write(n) slot to dump the structure into, or -1
+};
+
+struct __align__(16) CrewResult {  // what a team reports for the move it evaluated
+    double dE, eS, eE;             // eEnd - eStart; the two sums (tracing only)
+    int oob;                       // rejected by the 0.75 * spaceLen box, no energy evaluated
+    int pad_;
+};
+
 struct __align__(16) CrewChain {
     ChainCtrl ctrl;
     tr_schedule sch;
     uint32_t *mt;                  // global: [3][2][624] ping-pong blocks of this chain
     uint32_t ring[3][CREW_RING];
-    CrewDesc desc[2][2];           // [pair][candidate]: the control lane writes one pair while the team reads the other
-    // control lane -> team
-    int order;                     // ORD_* bits
-    int snap_slot;                 // REQ_TOTAL: write(n) slot to dump the structure into, or -1
-    int rd[3];                     // ring words consumed so far (published with ORD_FILL only)
-    int pad0_[3];
-    // team -> control lane
-    double dE;                     // REQ_MOVE: eEnd - eStart
-    int oob;                       // REQ_MOVE: rejected by the 0.75 * spaceLen box, no energy evaluated
-    int pad1_;
-    double eS, eE;                 // REQ_MOVE, tracing only
-    double etot;                   // REQ_TOTAL: Space.calcEnergy
+    CrewPlan plan[2];              // control lane -> team
+    CrewResult result[2];          // team -> control lane
+    double etot;                   // PLAN_TOTAL: Space.calcEnergy
     double bound;                  // 0.75 * spaceLen (Space.java:663,706)
+    int rd[3];                     // ring words consumed so far (published with PF_FILL only)
+    int pad0_;
     int wr[3];                     // ring words appended so far
-    int pad2_;
-    // team-private between rounds: what a commit of the move staged last round needs
+    int pad1_;
+    // team-private between rounds: what a commit of the move staged last needs
     int prev_p[TR_MAX_MOL_SITES];  // positions of its sites (-1 beyond s_m)
     double prev_v[3];              // its centre-of-mass shift
     int prev_m;                    // its particle, or -1 for a rotation (Molecule.rotateTemp leaves the centre of mass alone)
-    int pad3_;
+    int pad2_;
 };
+
+// The Metropolis test of Space.java:676-687 / :720-731 on a finished move.  Runs identically in the team that
+// evaluated the move (PLAN_AUTO) and in the chain's control lane (bookkeeping): same inputs, same code, same bits.
+// rand > exp(-dE / kT)  <=>  dE > -kT log(rand) is decided on the pre-computed threshold when dE is away from the
+// rounding noise of either form, else by the reference's own expression.
+__device__ __forceinline__ void crew_metropolis(int oob, double dE, bool tzero, bool metro_ok, double rnd, double thr, double grd,
+                                                double kBt, int &acc, int &drew)
+{
+    acc = oob ? 0 : 1; drew = 0;
+    if (!oob && dE > 0.0) {
+        drew = 1;                                       // the double is drawn before the T == 0 test
+        if (tzero) acc = 0;
+        else if (metro_ok && dE > thr + grd) acc = 0;
+        else if (metro_ok && dE < thr - grd) acc = 1;
+        else {
+            const double test = exp(__ddiv_rn(__dmul_rn(-1.0, dE), kBt));
+            if (rnd > test) acc = 0;
+        }
+    }
+}
 
 #ifdef TR_CREW_TIMING
 __device__ long long g_tm[8];
@@ -247,10 +277,12 @@ __device__ __forceinline__ void crew_ring_end(CrewChain *cs, const CrewWindow<L>
             cs->ring[w.s][(w.wr + i) & (CREW_RING - 1)] = mt_temper(v);
         }
     }
+    __syncwarp(mask);
     if (tl == 0) {
         MtCursor c;
         c.par = w.par; c.gen = w.load ? w.gen : w.fed + w.count; c.fed = w.fed + w.count;
         cs->ctrl.rng[w.s] = c;
+        __threadfence_block();                          // the control lane reads ahead as soon as it sees the new cursor
         cs->wr[w.s] = w.wr + w.count;
     }
     __syncwarp(mask);
@@ -273,7 +305,8 @@ __device__ __forceinline__ void crew_ring_fill(CrewChain *cs, int tl, unsigned m
 // Also leaves what a later commit needs (prev_p, prev_m, prev_v).
 template <int L, int SPL, int LJS, bool HAS_EXP, bool TRACE>
 __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewView &v, const DevSystem &sys, const CrewDesc &d,
-                                          const int (&info)[SPL], const double (&q)[SPL], int tl, unsigned mask)
+                                          const int (&info)[SPL], const double (&q)[SPL], int tl, unsigned mask, CrewResult *res,
+                                          double &dE_out, int &oob_out)
 {
     using TL = CrewTables<L, SPL>;
     static_assert(TR_MAX_MOL_SITES <= L, "one lane per site of the moved particle");
@@ -342,7 +375,8 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
     const long long tq1 = TMCLK();
     TMG(0, tq1 - tq0);
     if (any_oob) {
-        if (tl == 0) cs->oob = 1;
+        if (tl == 0) res->oob = 1;
+        dE_out = 0.0; oob_out = 1;
         return;
     }
     const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
@@ -359,10 +393,11 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
     const double dE = crew_team_sum<L>(eE - eS, mask);
     if (TRACE) { eS = crew_team_sum<L>(eS, mask); eE = crew_team_sum<L>(eE, mask); }
     if (tl == 0) {
-        cs->oob = 0;
-        cs->dE = dE;
-        if (TRACE) { cs->eS = eS; cs->eE = eE; }
+        res->oob = 0;
+        res->dE = dE;
+        if (TRACE) { res->eS = eS; res->eE = eE; }
     }
+    dE_out = dE; oob_out = 0;
     TMG(2, TMCLK() - tq2);
 }
 
@@ -483,9 +518,9 @@ __device__ __noinline__ void crew_finish_point(const KParams &P, CrewChain *cs, 
     }
 }
 
-// Does the point that just ended need Space.calcEnergy (movie frame energy or write(x+1))?  Sets the
-// dump slot for the energy warp.
-__device__ __forceinline__ bool crew_point_needs_total(const KParams &P, CrewChain *cs)
+// Does the point that just ended need Space.calcEnergy (movie frame energy or write(x+1))?  Returns the
+// dump slot for the energy team in `snap_slot`.
+__device__ __forceinline__ bool crew_point_needs_total(const KParams &P, CrewChain *cs, int &snap_slot)
 {
     const ChainCtrl *c = &cs->ctrl;
     const tr_schedule &sch = cs->sch;
@@ -495,7 +530,7 @@ __device__ __forceinline__ bool crew_point_needs_total(const KParams &P, CrewCha
     const bool tooth_end = c->y + 1 >= c->ptsPerTooth;
     const bool start_finale = tooth_end && (c->x == numTeeth - 1) && !c->isDoubleCycle && sch.finale;
     const bool snap = tooth_end && !start_finale;
-    cs->snap_slot = (snap && P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
+    snap_slot = (snap && P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
     return snap || (movie && P.points != nullptr);
 }
 
@@ -562,7 +597,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             if (tl == 0) {
                 v.cs->sch = P.sched[v.cs->ctrl.sched];
                 v.cs->mt = P.mt + (size_t)ch * 3 * 2 * MT_N;
-                v.cs->order = REQ_IDLE; v.cs->snap_slot = -1; v.cs->oob = 0; v.cs->prev_m = -1;
+                v.cs->plan[0].mode = PLAN_IDLE; v.cs->plan[1].mode = PLAN_IDLE; v.cs->prev_m = -1;
                 v.cs->bound = v.cs->ctrl.space_len * 0.75;
             }
             if (tl < 3) { v.cs->wr[tl] = 0; v.cs->rd[tl] = 0; }
@@ -581,6 +616,8 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
 #endif
     if (warp == 0) {
         // ================================================================ control warp: lane c <-> chain c
+        // Iteration r runs while the teams execute round r: it settles what they did in round r - 1 and writes
+        // plan[(r + 1) & 1], what they do in round r + 1.  One barrier per round.
         const bool mine = lane < nloc;
         const CrewView v = crew_view<L, SPL>(chains, mine ? lane : 0, stride, sys.n_mol, max_mol_sites);
         CrewChain *cs = v.cs;
@@ -597,25 +634,23 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
         int seg_moves = 0, seg_acc = 0, seg_eval = 0;            // since the last flush into c
         unsigned seg_sm = 0, seg_sm2 = 0;                         // pair evaluations = 2 * (S * sum s_m - sum s_m^2)
         int rdM = 0, rdS = 0, rdR = 0;                            // ring positions consumed so far
-        int wrM = 0, wrS = 0, wrR = 0;                            // snapshot of the producers' cursors, taken between barriers
+        int wrM = 0, wrS = 0, wrR = 0;                            // snapshot of the producers' cursors
         long long budget = P.max_moves > 0 ? P.max_moves : 0x7fffffffffffffffLL;
         bool live = mine && !c->done;
         bool hot = false;
         // pipeline state
-        bool inflight = false, pend_total = false, total_for_init = false, bk_pending = false, sel_pending = false, filled = false;
-        int commit_pending = 0, np = 0;                          // np: descriptor pair the next move is posted from
-        int refill_next = 3, refill_posted = 3;                  // stream the next order asks a window for / the one in flight
-        int cur_info = 0;                                        // move in flight: m | sm << 16 | rot << 21 | magwalk << 22 | (axis + 1) << 23
-        int sel = 0;                                             // candidate chosen by the last fast post
-        bool metro_ok = false, cand_ok = false;
-        double rnd = 0.0, thr = 0.0, grd = 0.0;                  // Metropolis draw of the move in flight and its dE threshold
+        int mode_prev = PLAN_IDLE, mode_cur = PLAN_IDLE;         // what the team did in round r - 1 / does in round r
+        bool total_for_init = false, filled = false;
+        int commit_pending = 0;
+        int refill_cur = 3;                                      // stream whose window is in flight in round r
+        int cur_info = 0;                                        // move of round r: m | sm << 16 | rot << 21 | magwalk << 22 | (axis + 1) << 23
+        int prev_info = 0;                                       // move of round r - 1
+        bool metro_ok = false;                                   // (rnd, thr, grd) belong to the move of round r - 1 when it is settled
+        double rnd = 0.0, thr = 0.0, grd = 0.0;
         CrewCommon cm; cm.sn = cm.cs = 0.0; cm.kindbit = cm.magw_rot = cm.magw_trans = 0; cm.axis = -1; cm.nR = 0; cm.ok = false;
         CrewPick cA, cB;                                         // successor if no Metropolis double is drawn / if one is
         cA.va = cA.vb = cA.vc = 0.0; cA.m = cA.off = cA.sm = cA.rot = cA.nS = 0; cA.ok = false;
         cB = cA;
-        // deferred bookkeeping of the move that just finished
-        int bk_info = 0, bk_acc = 0, bk_drew = 0, bk_oob = 0;
-        double bk_dE = 0.0, bk_rnd = 0.0, bk_eS = 0.0, bk_eE = 0.0;
 
         auto load_hot = [&]() {
             t = c->t; kBt = __dmul_rn(BOLTZMANN_CONSTANT, c->t);
@@ -623,7 +658,6 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             maxD = c->maxD; maxRot = c->maxRot; maxTmag = __dmul_rn(c->maxD, sch.magwalk_factor_trans);
             thr_rot = double_threshold52(c->probRot); thr_trans = double_threshold52(c->probTrans);
             z = c->z; mpp = sch.moves_per_point; hot = true;
-            metro_ok = false; cand_ok = false;
         };
         auto flush_hot = [&]() {
             c->z = z; c->running = running; c->totalE = totalE; c->totalSqE = totalSqE;
@@ -632,34 +666,6 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             c->moves += seg_moves; c->evaluated += seg_eval;
             c->pair_evals += 2LL * ((long long)S * seg_sm - seg_sm2);
             seg_moves = seg_acc = seg_eval = 0; seg_sm = seg_sm2 = 0;
-        };
-        // Main.java:215-223 for the finished move
-        auto bookkeep = [&]() {
-            running = __dadd_rn(running, bk_acc ? bk_dE : 0.0);
-            if (!sch.static_temp || z > sch.eq_configs) {
-                totalE = __dadd_rn(totalE, running);
-                totalSqE = __dadd_rn(totalSqE, __dmul_rn(running, running));
-            }
-            seg_acc += bk_acc;
-            if (!bk_oob) {
-                const int sm = (bk_info >> 16) & 31;
-                seg_eval++; seg_sm += (unsigned)sm; seg_sm2 += (unsigned)(sm * sm);
-            }
-            if (TRACE) {
-                const long long idx = c->moves + seg_moves;
-                if (idx < P.trace_moves) {
-                    tr_trace_rec r;
-                    r.mol = bk_info & 0xffff; r.kind = (int8_t)((bk_info >> 21) & 1); r.magwalk = (int8_t)((bk_info >> 22) & 1);
-                    r.bounds = (int8_t)bk_oob; r.accepted = (int8_t)bk_acc; r.axis = ((bk_info >> 23) & 7) - 1; r.drew_rand = bk_drew;
-                    r.e_start = bk_eS; r.e_end = bk_eE; r.dE = bk_dE;
-                    r.rand = bk_drew ? bk_rnd : __longlong_as_double(0x7ff8000000000000LL);
-                    r.temp = t; r.running = running;
-                    P.trace[chain * P.trace_moves + idx] = r;
-                }
-            }
-            seg_moves++; z++;
-            if (seg_moves >= (1 << 20)) flush_hot();
-            bk_pending = false;
         };
         auto ringM = [&](int pos) { return cs->ring[STREAM_M][pos & (CREW_RING - 1)]; };
         auto ringS = [&](int pos) { return cs->ring[STREAM_S][pos & (CREW_RING - 1)]; };
@@ -727,146 +733,107 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             k.ok = true;
         };
         // The descriptor the energy team reads for a drawn move.
-        auto write_desc = [&](const CrewPick &k, int pair, int which) {
+        auto write_desc = [&](const CrewPick &k, CrewDesc *dst) {
             CrewDesc d;
             const int axis = k.rot ? cm.axis : -1;
             d.va = k.rot ? cm.sn : k.va; d.vb = k.rot ? cm.cs : k.vb; d.vc = k.rot ? 0.0 : k.vc;
             d.m = k.m; d.off = k.off; d.info = k.sm | (k.rot << 8) | ((axis + 1) << 12); d.pad_ = 0;
-            cs->desc[pair][which] = d;
+            *dst = d;
         };
-        // The stream cursors move past a posted move's words; remember what bookkeeping and the trace need of it.
+        // The stream cursors move past a drawn move's words; remember what bookkeeping and the trace need of it.
         auto adopt = [&](const CrewPick &k) {
             const int magwalk = k.rot ? cm.magw_rot : cm.magw_trans;
             const int axis = k.rot ? cm.axis : -1;
             cur_info = k.m | (k.sm << 16) | (k.rot << 21) | (magwalk << 22) | ((axis + 1) << 23);
             rdS += k.nS; rdM += 4; rdR += k.rot ? cm.nR : 0;
         };
-        // Which ring gets the next window: the one with the fewest unread words if that is <= 32, never the one whose
-        // window is in flight (its cursor is not final yet); 3 = none.
+        // Which ring gets the window of round r + 1: the one with the fewest unread words if that is few enough, never
+        // the one whose window is in flight in round r (its cursor is not final yet); 3 = none.
         auto choose_refill = [&]() {
             int aM = wrM - rdM, aS = wrS - rdS, aR = wrR - rdR;
-            if (refill_posted == STREAM_M) aM = CREW_RING;
-            if (refill_posted == STREAM_S) aS = CREW_RING;
-            if (refill_posted == STREAM_R) aR = CREW_RING;
+            if (refill_cur == STREAM_M) aM = CREW_RING;
+            if (refill_cur == STREAM_S) aS = CREW_RING;
+            if (refill_cur == STREAM_R) aR = CREW_RING;
             int s = STREAM_M, amin = aM;
             if (aS < amin) { amin = aS; s = STREAM_S; }
             if (aR < amin) { amin = aR; s = STREAM_R; }
-            refill_next = amin <= CREW_RING_LOW ? s : 3;
+            return amin <= CREW_RING_LOW ? s : 3;
         };
         if (live) load_hot();
 
-        for (;;) {
+        for (int r = -1;; r++) {
             TM(const long long tm0 = clock64();)
-            // ------------------------------------------------ phase 1 (critical): the result of the round that just ended
-            int order = REQ_IDLE;
+            CrewPlan *pl = &cs->plan[(r + 1) & 1];
+            int mode = PLAN_IDLE;
             if (live) {
-                if (inflight) {
-                    // Metropolis: Space.java:668-689 / :711-733
-                    const int oob = cs->oob;
-                    const double dE = oob ? 0.0 : cs->dE;
-                    int acc = oob ? 0 : 1, drew = 0;
-                    if (!oob && dE > 0.0) {
-                        drew = 1;                                       // the double is drawn before the T == 0 test
-                        if (!metro_ok) rnd = crew_next_double(ringS(rdS), ringS(rdS + 1));
-                        if (t == 0.0) acc = 0;
-                        else if (metro_ok && dE > thr + grd) acc = 0;   // rand > exp(-dE / kT)  <=>  dE > -kT log(rand), decided
-                        else if (metro_ok && dE < thr - grd) acc = 1;   // away from the rounding noise of either form
-                        else {
-                            const double test = exp(__ddiv_rn(__dmul_rn(-1.0, dE), kBt));
-                            if (rnd > test) acc = 0;
-                        }
-                    }
-                    bk_info = cur_info; bk_acc = acc; bk_drew = drew; bk_oob = oob; bk_dE = dE; bk_rnd = rnd;
-                    if (TRACE) { bk_eS = oob ? 0.0 : cs->eS; bk_eE = oob ? 0.0 : cs->eE; }
-                    bk_pending = true;
-                    inflight = false; metro_ok = false;
+                wrM = cs->wr[STREAM_M]; wrS = cs->wr[STREAM_S]; wrR = cs->wr[STREAM_R];
+                // ---------------------------------------------- settle round r - 1
+                if (mode_prev == PLAN_AUTO || mode_prev == PLAN_MOVE) {
+                    // Metropolis: Space.java:668-689 / :711-733 (the team took the same decision if round r is PLAN_AUTO)
+                    const CrewResult *res = &cs->result[(r - 1) & 1];
+                    const int oob = res->oob;
+                    const double dE = oob ? 0.0 : res->dE;
+                    int acc, drew;
+                    if (!metro_ok && !oob && dE > 0.0) rnd = crew_next_double(ringS(rdS), ringS(rdS + 1));
+                    crew_metropolis(oob, dE, t == 0.0, metro_ok, rnd, thr, grd, kBt, acc, drew);
                     if (acc) commit_pending = 1;
                     rdS += 2 * drew;
-                    if (cand_ok) {
-                        // the successor was drawn ahead of time: post it now, settle the rest in the shadow of the energy phase
-                        sel = drew;
-                        order = REQ_MOVE | (sel ? ORD_SEL : 0) | (np ? ORD_PAR : 0) | (commit_pending ? ORD_COMMIT : 0) |
-                                (refill_next << ORD_REFILL_SHIFT);
-                        commit_pending = 0; np ^= 1;
-                        refill_posted = refill_next; refill_next = 3;
-                        sel_pending = true; inflight = true; budget--;
+                    // Main.java:215-223
+                    running = __dadd_rn(running, acc ? dE : 0.0);
+                    if (!sch.static_temp || z > sch.eq_configs) {
+                        totalE = __dadd_rn(totalE, running);
+                        totalSqE = __dadd_rn(totalSqE, __dmul_rn(running, running));
                     }
-                    cand_ok = false;
-                }
-                if (order == REQ_IDLE) {
-                    // -------------------------------------------- phase 2 (rare): everything that is not "next move of the same point"
-                    if (bk_pending) bookkeep();
-                    if (pend_total) {
-                        const double etot = cs->etot;
-                        pend_total = false;
-                        if (total_for_init) {
-                            // Main.java:64,71: write(0) and startingEnergy = calcEnergy()
-                            const int k = c->n_snaps;
-                            if (k < P.max_snaps) { P.snap_energy[chain * P.max_snaps + k] = etot; P.snap_tooth[chain * P.max_snaps + k] = 0; }
-                            c->n_snaps = k + 1;
-                            if (etot < c->min_energy) { c->min_energy = etot; c->min_tooth = 0; }
-                            c->start_energy = etot; c->running = etot; c->started = 1;
-                            c->delT = c->t / (double)(c->ptsPerTooth - 1);      // Main.java:188 for tooth 0
-                            total_for_init = false;
-                        } else {
-                            crew_finish_point(P, cs, chain, etot, true);
-                        }
-                        load_hot();
+                    seg_acc += acc;
+                    if (!oob) {
+                        const int sm = (prev_info >> 16) & 31;
+                        seg_eval++; seg_sm += (unsigned)sm; seg_sm2 += (unsigned)(sm * sm);
                     }
-                    int req = REQ_IDLE;
-                    if (!c->done && !c->started) {
-                        req = REQ_TOTAL; pend_total = true; total_for_init = true;
-                        cs->snap_slot = (P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
-                    } else if (!c->done && z >= mpp) {
-                        // end of the point: with a calcEnergy round first when its result is needed
-                        flush_hot();
-                        if (crew_point_needs_total(P, cs)) { req = REQ_TOTAL; pend_total = true; }
-                        else {
-                            crew_finish_point(P, cs, chain, 0.0, false);
-                            load_hot();
+                    if (TRACE) {
+                        const long long idx = c->moves + seg_moves;
+                        if (idx < P.trace_moves) {
+                            tr_trace_rec tr;
+                            tr.mol = prev_info & 0xffff; tr.kind = (int8_t)((prev_info >> 21) & 1); tr.magwalk = (int8_t)((prev_info >> 22) & 1);
+                            tr.bounds = (int8_t)oob; tr.accepted = (int8_t)acc; tr.axis = ((prev_info >> 23) & 7) - 1; tr.drew_rand = drew;
+                            tr.e_start = oob ? 0.0 : res->eS; tr.e_end = oob ? 0.0 : res->eE; tr.dE = dE;
+                            tr.rand = drew ? rnd : __longlong_as_double(0x7ff8000000000000LL);
+                            tr.temp = t; tr.running = running;
+                            P.trace[chain * P.trace_moves + idx] = tr;
                         }
                     }
-                    bool fill = false;
-                    if (!c->done && req == REQ_IDLE && budget > 0) {
-                        wrM = cs->wr[STREAM_M]; wrS = cs->wr[STREAM_S]; wrR = cs->wr[STREAM_R];
-                        draw_common();
-                        if (cm.ok) draw_pick(cA, rdS);
-                        if (cm.ok && cA.ok) {
-                            write_desc(cA, np, 0);
-                            adopt(cA);
-                            req = REQ_MOVE | (np ? ORD_PAR : 0);
-                            np ^= 1; inflight = true; budget--; filled = false;
-                        } else if (!filled) { fill = true; filled = true; }     // the rings ran low: one blocking fill, then retry
-                        else c->done = CHAIN_ABORT_RNG;
-                    }
-                    if (fill || (req == REQ_IDLE && commit_pending)) req = REQ_SYNC;      // (parked with an accepted move not yet committed)
-                    if (req != REQ_IDLE) {
-                        order = req | (commit_pending ? ORD_COMMIT : 0) | (fill ? ORD_FILL : 0) | ((fill ? 3 : refill_next) << ORD_REFILL_SHIFT);
+                    seg_moves++; z++;
+                    if (seg_moves >= (1 << 20)) flush_hot();
+                    if (mode_cur == PLAN_AUTO) {
+                        // the team is already evaluating the successor it chose by the same test
+                        CrewPick k = cA;
+                        if (drew) k = cB;
+                        adopt(k);
                         commit_pending = 0;
-                        refill_posted = fill ? 3 : refill_next; refill_next = 3;
-                        if (fill) { cs->rd[STREAM_M] = rdM; cs->rd[STREAM_S] = rdS; cs->rd[STREAM_R] = rdR; }
                     }
-                    if (c->done && order == REQ_IDLE) live = false;
+                } else if (mode_prev == PLAN_TOTAL) {
+                    const double etot = cs->etot;
+                    if (total_for_init) {
+                        // Main.java:64,71: write(0) and startingEnergy = calcEnergy()
+                        const int k = c->n_snaps;
+                        if (k < P.max_snaps) { P.snap_energy[chain * P.max_snaps + k] = etot; P.snap_tooth[chain * P.max_snaps + k] = 0; }
+                        c->n_snaps = k + 1;
+                        if (etot < c->min_energy) { c->min_energy = etot; c->min_tooth = 0; }
+                        c->start_energy = etot; c->running = etot; c->started = 1;
+                        c->delT = c->t / (double)(c->ptsPerTooth - 1);      // Main.java:188 for tooth 0
+                        total_for_init = false;
+                    } else {
+                        crew_finish_point(P, cs, chain, etot, true);
+                    }
+                    load_hot();
                 }
-                cs->order = order;
-                wrM = cs->wr[STREAM_M]; wrS = cs->wr[STREAM_S]; wrR = cs->wr[STREAM_R];     // stable: the producers are parked
-            } else if (mine) cs->order = REQ_IDLE;
-            const unsigned any = __ballot_sync(0xffffffffu, order != REQ_IDLE);
-            if (lane == 0) TL::alive(smem) = (int)any;
-            TM(const long long tm1 = clock64(); tm_a += tm1 - tm0; tm_rounds++;)
-            crew_bar(NT);                                   // B1: orders posted
-            if (!any) break;
-            // ------------------------------------------------ phase 3: in the shadow of the energy phase
-            if (live) {
-                if (sel_pending) {
-                    CrewPick k = cA;
-                    if (sel) k = cB;
-                    adopt(k);
-                    sel_pending = false;
-                }
-                if (bk_pending) bookkeep();
-                if (inflight) {
-                    // the Metropolis double the move in flight will draw if dE > 0, and its threshold on dE
+                metro_ok = false;
+
+                // ---------------------------------------------- plan round r + 1
+                int flags = 0, refill = 3, snap_slot = -1;
+                if (mode_cur == PLAN_AUTO || mode_cur == PLAN_MOVE) {
+                    // a move is being evaluated now: draw what its Metropolis test will need and both possible successors;
+                    // if all of that exists, the team may go on by itself
+                    bool chain_ok = false;
                     if (wrS - rdS >= 2) {
                         rnd = crew_next_double(ringS(rdS), ringS(rdS + 1));
                         if (t != 0.0) {
@@ -874,22 +841,68 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                             grd = (kBt + fabs(thr)) * 1e-11;
                         }
                         metro_ok = true;
+                        if (z + 1 < mpp && budget > 0) {         // the move in flight has a successor inside this point and this launch
+                            draw_common();
+                            if (cm.ok) { draw_pick(cA, rdS); draw_pick(cB, rdS + 2); }
+                            chain_ok = cm.ok && cA.ok && cB.ok;
+                        }
                     }
-                    // both possible successors, if the move in flight has one inside this point and this launch
-                    if (z + 1 < mpp && budget > 0) {
+                    if (chain_ok) {
+                        mode = PLAN_AUTO;
+                        write_desc(cA, &pl->cand[0]); write_desc(cB, &pl->cand[1]);
+                        pl->rnd = rnd; pl->thr = thr; pl->grd = grd; pl->kBt = kBt;
+                        flags = (t == 0.0) ? PF_TZERO : 0;
+                        refill = choose_refill();
+                        budget--;
+                    }
+                    prev_info = cur_info;
+                } else if (mode_cur == PLAN_IDLE) {
+                    // nothing is running: everything that is not "next move of the same point" is decided here
+                    bool fill = false;
+                    if (!c->done && !c->started) {
+                        mode = PLAN_TOTAL; total_for_init = true;
+                        snap_slot = (P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
+                    } else if (!c->done && z >= mpp) {
+                        // end of the point: with a calcEnergy round first when its result is needed
+                        flush_hot();
+                        if (crew_point_needs_total(P, cs, snap_slot)) mode = PLAN_TOTAL;
+                        else {
+                            crew_finish_point(P, cs, chain, 0.0, false);
+                            load_hot();
+                        }
+                    }
+                    if (!c->done && mode == PLAN_IDLE && budget > 0) {
                         draw_common();
-                        if (cm.ok) { draw_pick(cA, rdS); draw_pick(cB, rdS + 2); }
-                        cand_ok = cm.ok && cA.ok && cB.ok;
-                        if (cand_ok) { write_desc(cA, np, 0); write_desc(cB, np, 1); }
+                        if (cm.ok) draw_pick(cA, rdS);
+                        if (cm.ok && cA.ok) {
+                            write_desc(cA, &pl->cand[0]);
+                            adopt(cA);
+                            mode = PLAN_MOVE; budget--; filled = false;
+                        } else if (!filled) { fill = true; filled = true; }     // the rings ran low: one blocking fill, then retry
+                        else c->done = CHAIN_ABORT_RNG;
                     }
-                    choose_refill();
+                    if (fill || (mode == PLAN_IDLE && commit_pending)) mode = PLAN_SYNC;   // (parked with an accepted move not yet committed)
+                    if (mode != PLAN_IDLE) {
+                        flags = (commit_pending ? PF_COMMIT : 0) | (fill ? PF_FILL : 0);
+                        commit_pending = 0;
+                        refill = fill ? 3 : choose_refill();
+                        if (fill) { cs->rd[STREAM_M] = rdM; cs->rd[STREAM_S] = rdS; cs->rd[STREAM_R] = rdR; }
+                    }
+                    if (c->done && mode == PLAN_IDLE) live = false;
                 }
-            }
-            TM(const long long tm2 = clock64(); tm_b += tm2 - tm1;)
-            crew_bar(NT);                                   // B2: results posted
-            TM(tm_c += clock64() - tm2;)
+                // (PLAN_TOTAL / PLAN_SYNC running now: wait for it)
+                pl->mode = mode; pl->flags = flags; pl->refill = refill; pl->snap_slot = snap_slot;
+                refill_cur = refill;
+            } else if (mine) pl->mode = PLAN_IDLE;
+            const unsigned any = __ballot_sync(0xffffffffu, mode != PLAN_IDLE || mode_cur != PLAN_IDLE);
+            mode_prev = mode_cur; mode_cur = mode;
+            if (lane == 0) TL::alive(smem) = (int)any;
+            TM(const long long tm1 = clock64(); tm_a += tm1 - tm0; tm_rounds++;)
+            crew_bar(NT);
+            TM(tm_c += clock64() - tm1;)
+            if (!any) break;
         }
-        TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 control: rounds %lld critical %lld shadow(incl B1) %lld waitB2 %lld cycles/round\n", tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds, tm_c / tm_rounds);)
+        TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 control: rounds %lld work %lld wait %lld cycles/round\n", tm_rounds, tm_a / tm_rounds, tm_c / tm_rounds);)
         // park the chain: counters into c, unread ring words back to the stream cursors
         if (mine) {
             if (hot) flush_hot();
@@ -907,13 +920,16 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
         double q[SPL];
 #pragma unroll
         for (int k = 0; k < SPL; k++) { info[k] = TL::pos_info(smem, tl + L * k); q[k] = TL::qpos(smem, tl + L * k); }
-        for (;;) {
-            crew_bar(NT);                                   // B1
+        double last_dE = 0.0;                               // result of the move this team evaluated last
+        int last_oob = 0;
+        crew_bar(NT);                                       // plan[0] is written
+        for (int r = 0;; r++) {
             if (TL::alive(smem) == 0) break;
             TM(const long long tm0 = clock64(); tm_rounds++;)
             if (has) {
-                const int order = cs->order;
-                // what a commit needs sits at fixed addresses: these loads do not wait for the order word
+                const CrewPlan *pl = &cs->plan[r & 1];
+                const int mode = pl->mode;
+                // what a commit needs sits at fixed addresses: these loads do not wait for the plan
                 int pp = -1;
                 double cnx = 0.0, cny = 0.0, cnz = 0.0;
                 if (tl < TR_MAX_MOL_SITES) {
@@ -921,13 +937,19 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     const StageSite *st = &v.stage[tl < max_mol_sites ? tl : 0];
                     cnx = st->nx; cny = st->ny; cnz = st->nz;
                 }
-                const int req = order & ORD_REQ;
-                if (req != REQ_IDLE) {
+                if (mode != PLAN_IDLE) {
                     TM(const long long tm1 = clock64();)
-                    const CrewWindow<L> w = crew_ring_begin<L>(cs, (order >> ORD_REFILL_SHIFT) & 3, tl);    // loads fly while the move is evaluated
+                    const int flags = pl->flags;
+                    const CrewWindow<L> w = crew_ring_begin<L>(cs, pl->refill, tl);    // loads fly while the move is evaluated
                     TMG(3, TMCLK() - tm1);
-                    if (order & ORD_COMMIT) {
-                        // setTemps (Molecule.java:128-135) of the move staged last round
+                    int commit = flags & PF_COMMIT, which = 0;
+                    if (mode == PLAN_AUTO) {
+                        int acc, drew;
+                        crew_metropolis(last_oob, last_dE, (flags & PF_TZERO) != 0, true, pl->rnd, pl->thr, pl->grd, pl->kBt, acc, drew);
+                        commit = acc; which = drew;
+                    }
+                    if (commit) {
+                        // setTemps (Molecule.java:128-135) of the move staged last
                         if (pp >= 0) { v.xs[pp] = cnx; v.ys[pp] = cny; v.zs[pp] = cnz; }
                         if (tl == 0) {
                             const int pm = cs->prev_m;
@@ -940,24 +962,24 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                         __syncwarp(mask);
                     }
                     TMG(4, TMCLK() - tm1);
-                    if (req == REQ_MOVE) {
-                        const CrewDesc d = cs->desc[(order & ORD_PAR) ? 1 : 0][(order & ORD_SEL) ? 1 : 0];
-                        crew_move<L, SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, d, info, q, tl, mask);
-                    } else if (req == REQ_TOTAL) {
+                    if (mode == PLAN_AUTO || mode == PLAN_MOVE) {
+                        const CrewDesc d = pl->cand[which];
+                        crew_move<L, SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, d, info, q, tl, mask, &cs->result[r & 1], last_dE, last_oob);
+                    } else if (mode == PLAN_TOTAL) {
                         const double e = crew_total_energy<L, SPL, HAS_EXP>(smem, v, sys, info, q, tl, mask);
                         if (tl == 0) cs->etot = e;
-                        const int k = cs->snap_slot;
+                        const int k = pl->snap_slot;
                         if (k >= 0)
                             crew_sites_to_global<L, SPL>(v, P.snap_sites + ((size_t)(chain0 + c) * P.max_snaps + k) * (size_t)sys.n_sites * 3, sys, tl);
                     }
                     TM(const long long tm2 = clock64(); tm_a += tm2 - tm1;)
                     crew_ring_end<L>(cs, w, tl, mask);
-                    if (order & ORD_FILL) crew_ring_fill<L>(cs, tl, mask);
+                    if (flags & PF_FILL) crew_ring_fill<L>(cs, tl, mask);
                     TM(tm_b += clock64() - tm2;)
                 }
             }
             TM(tm_c += clock64() - tm0;)
-            crew_bar(NT);                                   // B2
+            crew_bar(NT);
         }
         TM(if (blockIdx.x == 3 && threadIdx.x == 32) printf("block 3 warp 1 per round: geometry %lld pair %lld reduce %lld ring_begin %lld (begin+commit %lld)\n", g_tm[0] / tm_rounds, g_tm[1] / tm_rounds, g_tm[2] / tm_rounds, g_tm[3] / tm_rounds, g_tm[4] / tm_rounds);)
         TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 warp %d: rounds %lld busy %lld (work %lld ring_end %lld) cycles/round\n", warp, tm_rounds, tm_c / tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds);)
