@@ -216,7 +216,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dbase, cfg, system = load_problem(args)
-    cpg = args.chains_per_gpu or (CHAINS_PER_GPU if args.workload != "h2o256" else 2 * 148)
+    cpg = args.chains_per_gpu or (CHAINS_PER_GPU if args.workload != "h2o256" else 6 * 148)
     first = rank * cpg
     seeds = np.arange(1000 + first, 1000 + first + cpg, dtype=np.int64)
     pinned_seeds = torch.from_numpy(seeds).pin_memory()
@@ -313,7 +313,7 @@ def run_ours(args):
     steps = args.steps
     value = moves_all * steps / (ms_dev * 1e-3)
     e2e_value = moves_all * steps / (ms_e2e * 1e-3)
-    # roofline of the dominant kernel (anneal_kernel): executed pair evaluations x 19 flops over its device time, per GPU
+    # roofline of the dominant kernel (crew_kernel / anneal_kernel): executed pair evaluations x 19 flops over its device time, per GPU
     achieved_tflops = (pairs_all / world) * steps * FLOPS_PER_PAIR / (ms_kernel * 1e-3) / 1e12
 
     if rank == 0:
@@ -329,7 +329,8 @@ def run_ours(args):
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved_tflops / peak_tflops, "traffic": None,
-                "kernel": "anneal_kernel", "flops_per_pair_eval": FLOPS_PER_PAIR,
+                "kernel": "crew_kernel" if (args.threads_per_chain == 0 and system.n_sites <= 64) else "anneal_kernel",
+                "flops_per_pair_eval": FLOPS_PER_PAIR,
                 "pair_evals_per_launch": pairs_all / world,
                 "peak_source": f"DFMA micro-benchmark run live on this device (tr_measure_fp64_peak), implied SM clock {peak_clock:.0f} MHz; "
                                "MEASURED_PEAKS.json has no FP64 figure",

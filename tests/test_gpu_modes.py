@@ -231,18 +231,22 @@ def test_ragged_chain_counts(engine, dbase, sample_cfg, n_chains):
 
 @pytest.mark.parametrize("name,tpcs", [("h2o20", (16, 32, 128)), ("mixed64", (32, 256)), ("sample8", (16, 32))])
 def test_every_kernel_variant_takes_the_same_decisions(engine, dbase, sample_cfg, name, tpcs):
-    """threads_per_chain = 0 (crew kernel), 16 / 32 (team kernels) and 128 / 256 (block per chain) are the same Markov
-    chain: identical decision traces, energies within the bar."""
+    """threads_per_chain = 0 (automatic: crew kernel up to 64 sites, else a team kernel), the crew kernel forced, 16 / 32
+    (team kernels) and 128 / 256 (block per chain) are the same Markov chain: identical decision traces, energies
+    within the bar."""
     cfg = workload_config(sample_cfg, name, movePerPt=500, ptsPerTooth=3, numTeeth=2, maxTemp=700.0)
     seeds = [300, 301, 302]
     n = cfg.total_moves()
     system = system_from_config(dbase, cfg)
     ref = None
-    for tpc in (0,) + tuple(tpcs):
+    for tpc in (0, "crew") + tuple(tpcs):
+        if tpc == "crew":                 # the warp-specialised kernel also where the automatic choice prefers a team kernel
+            os.environ["TR_FORCE_CREW"] = "1"
         engine.set_system(system)
         engine.set_schedules(cfg)
-        engine.set_options(trace_moves=n, threads_per_chain=tpc)
+        engine.set_options(trace_moves=n, threads_per_chain=0 if tpc == "crew" else tpc)
         engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+        os.environ.pop("TR_FORCE_CREW", None)
         engine.run(0)
         tr, mins = engine.trace(), engine.pack_minima()
         if ref is None:

@@ -1,11 +1,14 @@
-run() { # name lib extra-env...
-  name=$1; lib=$2; shift 2
-  env "$@" TR_LIB=$lib timeout 120 python bench.py --steps 2 --warmup 1 --moves-per-point 500 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', round(d['value']/1e9,4), round(d['roofline']['frac'],4))"
+run() { # name args...
+  name=$1; shift
+  timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline "$@" 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', d['config']['chains_per_gpu'], round(d['value']/1e6,2), 'M moves/s frac', round(d['roofline']['frac'],4))"
 }
-run base transrot_b200/libtransrot_b200.so X=1
-run e4 exp_libs/lib_e4.so X=1
-run e4_c8 exp_libs/lib_e4.so TR_CREW_C=8
-run e7b3 exp_libs/lib_e7b3.so X=1
-run e7b3_c10 exp_libs/lib_e7b3.so TR_CREW_C=10
-run e14 exp_libs/lib_e14.so X=1
-run base_c12 transrot_b200/libtransrot_b200.so TR_CREW_C=12
+run nh4cl32_crew --workload nh4cl32 --moves-per-point 500
+run nh4cl32_team32 --workload nh4cl32 --moves-per-point 500 --threads-per-chain 32
+run mixed64_team32 --workload mixed64 --moves-per-point 500 --threads-per-chain 32
+run sample8_team16 --workload sample8 --moves-per-point 500 --threads-per-chain 16
+run h2o20_team16 --workload h2o20 --moves-per-point 500 --threads-per-chain 16
+run h2o256_128 --workload h2o256 --moves-per-point 100 --threads-per-chain 128
+run h2o256_256 --workload h2o256 --moves-per-point 100 --threads-per-chain 256
+run h2o256_256_592 --workload h2o256 --moves-per-point 100 --threads-per-chain 256 --chains-per-gpu 592
+run h2o256_128_888 --workload h2o256 --moves-per-point 100 --threads-per-chain 128 --chains-per-gpu 888
+run h2o256_128_1184 --workload h2o256 --moves-per-point 100 --threads-per-chain 128 --chains-per-gpu 1184

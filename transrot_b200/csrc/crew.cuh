@@ -84,7 +84,7 @@ struct __align__(16) CrewChain {
     int pad1_;
     // team-private between rounds: what a commit of the move staged last needs
     int prev_p[TR_MAX_MOL_SITES];  // positions of its sites (-1 beyond s_m)
-    double prev_v[3];              // its centre-of-mass shift
+    double prev_v[3];              // its centre of mass if it is committed (m.x = m.tempx)
     int prev_m;                    // its particle, or -1 for a rotation (Molecule.rotateTemp leaves the centre of mass alone)
     int pad2_;
 };
@@ -312,7 +312,7 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
     static_assert(TR_MAX_MOL_SITES <= L, "one lane per site of the moved particle");
     CrewChain *cs = v.cs;
     const int m = d.m, sm = desc_sm(d.info), rot = desc_rot(d.info), axis = desc_axis(d.info);
-    const long long tq0 = TMCLK();
+    [[maybe_unused]] const long long tq0 = TMCLK();
     // this lane's positions; those of m itself are taken out by a far-away x, a zero charge and the all-zero table column
     double x[SPL], y[SPL], z[SPL], qm[SPL];
     int col[SPL];
@@ -367,12 +367,16 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
         cs->prev_p[tl] = p;
         if (tl == 0) {
             cs->prev_m = rot ? -1 : m;
-            cs->prev_v[0] = d.va; cs->prev_v[1] = d.vb; cs->prev_v[2] = d.vc;
+            if (!rot) {
+                cs->prev_v[0] = __dadd_rn(v.com[3 * m], d.va);
+                cs->prev_v[1] = __dadd_rn(v.com[3 * m + 1], d.vb);
+                cs->prev_v[2] = __dadd_rn(v.com[3 * m + 2], d.vc);
+            }
         }
     }
     const bool any_oob = (__ballot_sync(mask, oob) & mask) != 0u;
     __syncwarp(mask);                                       // staging stores before the broadcast reads below
-    const long long tq1 = TMCLK();
+    [[maybe_unused]] const long long tq1 = TMCLK();
     TMG(0, tq1 - tq0);
     if (any_oob) {
         if (tl == 0) res->oob = 1;
@@ -387,7 +391,7 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
         else if (LJS > 0 && st.lj) stage_site_energy<SPL, LJS, 1>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
         else stage_site_energy<SPL, 0, 0>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
     }
-    const long long tq2 = TMCLK();
+    [[maybe_unused]] const long long tq2 = TMCLK();
     TMG(1, tq2 - tq1);
     // differenced per lane before the reduction (less cancellation than reducing the two ~100x larger sums)
     const double dE = crew_team_sum<L>(eE - eS, mask);
@@ -613,6 +617,11 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
 #define TM(...) __VA_ARGS__
 #else
 #define TM(...)
+#endif
+#ifdef TR_CREW_STAGGER
+    // co-resident blocks otherwise fall into step and their FP64 bursts (the pair phase) collide
+    if ((blockIdx.x / P.sm_count) & 1) { const long long t0 = clock64(); while (clock64() - t0 < TR_CREW_STAGGER) { } }
+    __syncthreads();
 #endif
     if (warp == 0) {
         // ================================================================ control warp: lane c <-> chain c
@@ -930,13 +939,14 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                 const CrewPlan *pl = &cs->plan[r & 1];
                 const int mode = pl->mode;
                 // what a commit needs sits at fixed addresses: these loads do not wait for the plan
-                int pp = -1;
-                double cnx = 0.0, cny = 0.0, cnz = 0.0;
+                int pp = -1, pm = -1;
+                double cnx = 0.0, cny = 0.0, cnz = 0.0, cmx = 0.0, cmy = 0.0, cmz = 0.0;
                 if (tl < TR_MAX_MOL_SITES) {
                     pp = cs->prev_p[tl];
                     const StageSite *st = &v.stage[tl < max_mol_sites ? tl : 0];
                     cnx = st->nx; cny = st->ny; cnz = st->nz;
                 }
+                if (tl == 0) { pm = cs->prev_m; cmx = cs->prev_v[0]; cmy = cs->prev_v[1]; cmz = cs->prev_v[2]; }
                 if (mode != PLAN_IDLE) {
                     TM(const long long tm1 = clock64();)
                     const int flags = pl->flags;
@@ -951,14 +961,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     if (commit) {
                         // setTemps (Molecule.java:128-135) of the move staged last
                         if (pp >= 0) { v.xs[pp] = cnx; v.ys[pp] = cny; v.zs[pp] = cnz; }
-                        if (tl == 0) {
-                            const int pm = cs->prev_m;
-                            if (pm >= 0) {                  // m.x = m.tempx
-                                v.com[3 * pm] = __dadd_rn(v.com[3 * pm], cs->prev_v[0]);
-                                v.com[3 * pm + 1] = __dadd_rn(v.com[3 * pm + 1], cs->prev_v[1]);
-                                v.com[3 * pm + 2] = __dadd_rn(v.com[3 * pm + 2], cs->prev_v[2]);
-                            }
-                        }
+                        if (pm >= 0) { v.com[3 * pm] = cmx; v.com[3 * pm + 1] = cmy; v.com[3 * pm + 2] = cmz; }    // m.x = m.tempx
                         __syncwarp(mask);
                     }
                     TMG(4, TMCLK() - tm1);

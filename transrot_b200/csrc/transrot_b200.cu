@@ -399,7 +399,9 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
         return fail(ctx, TR_ELIMIT, "Error: %d sites do not fit %d threads per chain (limit %d sites)", ctx->sys.n_sites,
                     ctx->threads_per_chain, TR_MAX_SITES);
     ctx->variant = v;
-    ctx->use_crew = ctx->threads_per_chain == 0 && v.W == 1;
+    // the crew kernel wins while a chain fits a half-warp team (<= 64 sites: 1.3 vs 1.1 G moves/s on (H2O)20); for
+    // 65..192 sites the warp-per-chain team kernel is ahead (0.55 vs 0.45 G moves/s on (NH4Cl)32), TR_FORCE_CREW=1 overrides
+    ctx->use_crew = ctx->threads_per_chain == 0 && v.W == 1 && (v.L == 16 || env_int("TR_FORCE_CREW", 0) != 0);
     if (int r = prepare_variant(ctx, v)) return r;
     int smem = 0;
     if (ctx->use_crew) {
@@ -760,6 +762,7 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     P.trace_moves = ctx->trace_moves;
     P.max_points = ctx->max_points;
     P.max_snaps = ctx->max_snaps;
+    P.sm_count = ctx->sm_count;
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->use_crew) {
         if (int r = launch_crew(ctx, P)) return r;
