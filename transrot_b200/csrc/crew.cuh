@@ -7,22 +7,29 @@
 // control flow (ring draws, u -> double conversions, sincos, Metropolis exp, bookkeeping): ~500
 // issue slots per move that serve ONE chain, as many as the pair arithmetic itself (ncu: FP64 pipe
 // 38 % active, issue 53-68 %).  Here a block owns C chains and splits the work by warp role:
-//   * warp 0, the CONTROL warp: lane c runs chain c's control flow, so those instructions serve up
-//     to 32 chains at once.  Part A finishes the pending move (Metropolis test, commit, the
-//     sawtoothAnneal accumulators, end-of-point / end-of-tooth logic); part B draws the next move,
-//     builds the trial geometry of its s_m sites into the chain's staging area and posts a request.
-//   * warps 1..E, the ENERGY warps: warp-per-chain (lane = position mod 32).  For a posted move they
-//     evaluate the staged sites against their positions in FP64 and shuffle-reduce eEnd - eStart into
-//     the chain's mailbox; they keep the chain's three MT19937 rings topped up (>= 33 unread words per
-//     stream after every round, so the control lane never waits for the generator); and they serve the
-//     rare cooperative requests (Space.calcEnergy for write(n) / writeMovie, structure dumps).
-// Two named barriers per round separate the phases.  Several blocks per SM overlap one block's
-// control phase with another's energy phase.
+//   * warp 0, the CONTROL warp: lane c runs chain c's control flow, so those instructions serve up to
+//     32 chains at once - and it runs ONE ROUND BEHIND the energy teams.  While the teams evaluate the
+//     move of round r, lane c settles the move of round r - 1 (Metropolis test, the sawtoothAnneal
+//     accumulators, trace record) and draws everything round r + 1 can need: the Metropolis double of
+//     the move in flight with its threshold on dE, and BOTH possible successors (the S-stream position
+//     of the next pick depends on whether that double gets drawn: Space.java:720-721), sincos included.
+//     It posts them as a PLAN.  Everything that is not "next move of the same point" (end of point /
+//     tooth, calcEnergy rounds, finale, budget, low rings) is an explicit plan, at the cost of a bubble
+//     round for that chain only.
+//   * warps 1..E, the ENERGY teams: L = 16 or 32 lanes per chain (two chains per warp for L = 16), lane =
+//     position mod L.  A team settles its own previous move with the posted threshold (same code, same
+//     bits as the control lane), commits it if accepted (setTemps), builds the trial geometry of the
+//     chosen successor (lane a < s_m <-> site a) with the 0.75 * spaceLen box test, evaluates the staged
+//     sites against its positions in FP64 (anneal.cuh: group_energy) and shuffle-reduces eEnd - eStart.
+//     It also appends the 32-word MT19937 window the plan asks for (global loads issued before the pair
+//     arithmetic, twisted and tempered after it) and serves calcEnergy / structure-dump rounds.
+// One named barrier per round.  Plans and results are double-buffered by round parity: nobody reads
+// what the other side is writing.
 //
-// Shared memory per chain: CrewChain (ChainCtrl, schedule, rings, mailbox) + stage[max s_m] +
-// com[N][3] + x[NPOS] y[NPOS] z[NPOS] (SoA: an energy lane reads position lane + 32 k without bank
-// conflicts; charges and table columns are chain-independent and live in the energy lanes'
-// registers).  Positions are ordered Lennard-Jones sites first, as in anneal.cuh.
+// Shared memory per chain: CrewChain (ChainCtrl, schedule, three 128-word rings of tempered words, two
+// plans, two results) + stage[max s_m] + com[N][3] + x[NPOS] y[NPOS] z[NPOS] (SoA: a team lane reads
+// position lane + L k without bank conflicts; charges and table columns are chain-independent and live
+// in the team lanes' registers).  Positions are ordered Lennard-Jones sites first, as in anneal.cuh.
 #pragma once
 #include "anneal.cuh"
 
@@ -111,7 +118,7 @@ __device__ __forceinline__ void crew_metropolis(int oob, double dE, bool tzero, 
 
 #ifdef TR_CREW_TIMING
 __device__ long long g_tm[8];
-#define TMG(i, expr) do { if (blockIdx.x == 3 && threadIdx.x == 32) g_tm[i] += (expr); } while (0)
+#define TMG(i, expr) do { } while (0)
 #define TMCLK() clock64()
 #else
 #define TMG(i, expr) do { } while (0)
@@ -618,11 +625,6 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
 #else
 #define TM(...)
 #endif
-#ifdef TR_CREW_STAGGER
-    // co-resident blocks otherwise fall into step and their FP64 bursts (the pair phase) collide
-    if ((blockIdx.x / P.sm_count) & 1) { const long long t0 = clock64(); while (clock64() - t0 < TR_CREW_STAGGER) { } }
-    __syncthreads();
-#endif
     if (warp == 0) {
         // ================================================================ control warp: lane c <-> chain c
         // Iteration r runs while the teams execute round r: it settles what they did in round r - 1 and writes
@@ -770,6 +772,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
         };
         if (live) load_hot();
 
+        TM(const long long tm_start = clock64();)
         for (int r = -1;; r++) {
             TM(const long long tm0 = clock64();)
             CrewPlan *pl = &cs->plan[(r + 1) & 1];
@@ -911,7 +914,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             TM(tm_c += clock64() - tm1;)
             if (!any) break;
         }
-        TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 control: rounds %lld work %lld wait %lld cycles/round\n", tm_rounds, tm_a / tm_rounds, tm_c / tm_rounds);)
+        TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 control: rounds %lld work %lld wait %lld total %lld cycles/round\n", tm_rounds, tm_a / tm_rounds, tm_c / tm_rounds, (clock64() - tm_start) / tm_rounds);)
         // park the chain: counters into c, unread ring words back to the stream cursors
         if (mine) {
             if (hot) flush_hot();

@@ -77,7 +77,6 @@ struct KParams {
     long long max_moves;        // <= 0: run to completion
     long long trace_moves;
     int max_points, max_snaps;
-    int sm_count;               // SMs of the device (block placement heuristics)
 };
 
 enum { STREAM_M = 0, STREAM_S = 1, STREAM_R = 2 };

@@ -762,7 +762,6 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     P.trace_moves = ctx->trace_moves;
     P.max_points = ctx->max_points;
     P.max_snaps = ctx->max_snaps;
-    P.sm_count = ctx->sm_count;
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->use_crew) {
         if (int r = launch_crew(ctx, P)) return r;
