@@ -117,12 +117,15 @@ __device__ __forceinline__ void crew_metropolis(int oob, double dE, bool tzero, 
 }
 
 #ifdef TR_CREW_TIMING
-__device__ long long g_tm[8];
-#define TMG(i, expr) do { } while (0)
+#define TMG(i, expr) do { tmv[i] += (expr); } while (0)
 #define TMCLK() clock64()
+#define TMV_PARAM , long long *tmv
+#define TMV_ARG , tmv
 #else
 #define TMG(i, expr) do { } while (0)
 #define TMCLK() 0LL
+#define TMV_PARAM
+#define TMV_ARG
 #endif
 
 constexpr int CREW_BAR = 1;        // named barrier used by both roles
@@ -313,7 +316,7 @@ __device__ __forceinline__ void crew_ring_fill(CrewChain *cs, int tl, unsigned m
 template <int L, int SPL, int LJS, bool HAS_EXP, bool TRACE>
 __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewView &v, const DevSystem &sys, const CrewDesc &d,
                                           const int (&info)[SPL], const double (&q)[SPL], int tl, unsigned mask, CrewResult *res,
-                                          double &dE_out, int &oob_out)
+                                          double &dE_out, int &oob_out TMV_PARAM)
 {
     using TL = CrewTables<L, SPL>;
     static_assert(TR_MAX_MOL_SITES <= L, "one lane per site of the moved particle");
@@ -932,6 +935,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
         double q[SPL];
 #pragma unroll
         for (int k = 0; k < SPL; k++) { info[k] = TL::pos_info(smem, tl + L * k); q[k] = TL::qpos(smem, tl + L * k); }
+        TM(long long tmv[8] = {0, 0, 0, 0, 0, 0, 0, 0};)
         double last_dE = 0.0;                               // result of the move this team evaluated last
         int last_oob = 0;
         crew_bar(NT);                                       // plan[0] is written
@@ -970,7 +974,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     TMG(4, TMCLK() - tm1);
                     if (mode == PLAN_AUTO || mode == PLAN_MOVE) {
                         const CrewDesc d = pl->cand[which];
-                        crew_move<L, SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, d, info, q, tl, mask, &cs->result[r & 1], last_dE, last_oob);
+                        crew_move<L, SPL, LJS, HAS_EXP, TRACE>(smem, v, sys, d, info, q, tl, mask, &cs->result[r & 1], last_dE, last_oob TMV_ARG);
                     } else if (mode == PLAN_TOTAL) {
                         const double e = crew_total_energy<L, SPL, HAS_EXP>(smem, v, sys, info, q, tl, mask);
                         if (tl == 0) cs->etot = e;
@@ -987,7 +991,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             TM(tm_c += clock64() - tm0;)
             crew_bar(NT);
         }
-        TM(if (blockIdx.x == 3 && threadIdx.x == 32) printf("block 3 warp 1 per round: geometry %lld pair %lld reduce %lld ring_begin %lld (begin+commit %lld)\n", g_tm[0] / tm_rounds, g_tm[1] / tm_rounds, g_tm[2] / tm_rounds, g_tm[3] / tm_rounds, g_tm[4] / tm_rounds);)
+        TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 warp %d per round: geometry %lld pair %lld reduce %lld ring_begin %lld (begin+commit %lld)\n", warp, tmv[0] / tm_rounds, tmv[1] / tm_rounds, tmv[2] / tm_rounds, tmv[3] / tm_rounds, tmv[4] / tm_rounds);)
         TM(if (blockIdx.x == 3 && lane == 0) printf("block 3 warp %d: rounds %lld busy %lld (work %lld ring_end %lld) cycles/round\n", warp, tm_rounds, tm_c / tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds);)
     }
     __syncthreads();
