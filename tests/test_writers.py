@@ -1,0 +1,61 @@
+"""Output-file formats (reference Space.write / writeMovie / writeAcceptance / heat capacities): JVM number formatting
+and the restart round trip OutputN.xyz -> Input.xyz (Space.java:187, 550-612)."""
+import os
+
+import numpy as np
+import pytest
+
+from transrot_b200 import (
+    format_acceptance_line, format_heat_capacity_line, format_movie_frame, format_output_xyz, java_double_to_string,
+    precision_round, read_input,
+)
+
+
+@pytest.mark.parametrize("value,text", [
+    (1.0, "1.0"), (100.0, "100.0"), (1234567.0, "1234567.0"), (1.0e7, "1.0E7"), (123456789.0, "1.23456789E8"),
+    (0.001, "0.001"), (9.999e-4, "9.999E-4"), (1.5e-10, "1.5E-10"), (-0.5, "-0.5"), (0.05, "0.05"), (0.0, "0.0"),
+    (-460.8203874165545, "-460.8203874165545"), (1.1368683772161603e-12, "1.1368683772161603E-12"),
+    (float("nan"), "NaN"), (float("inf"), "Infinity"),
+])
+def test_java_double_to_string(value, text):
+    assert java_double_to_string(value) == text
+
+
+def test_precision_round_is_half_up_on_the_decimal_string():
+    assert precision_round(1.00000000005, 10) == 1.0000000001       # HALF_UP on "1.00000000005", not banker's / binary
+    assert precision_round(-1.00000000005, 10) == -1.0000000001
+    assert precision_round(2.5, 0) == 3.0 and precision_round(0.12345678904, 10) == 0.123456789
+
+
+def test_output_xyz_format_and_restart_round_trip(dbase, golden_dir, tmp_path):
+    system, xyz = read_input(os.path.join(golden_dir, "sample8.input.xyz"), dbase)
+    text = format_output_xyz(system, xyz, -460.8203874165545)
+    lines = text.split("\n")
+    assert lines[0] == "          24" and lines[1] == "Energy: -460.8203874165545 Kcal/mole  4 NH4+ | 4 Cl-"
+    assert len(lines) == 2 + 24 + 1 and lines[-1] == ""
+    # symbol padded to two columns, integer part right-aligned in four, ten decimals
+    sym, *cols = lines[2].split("  ")
+    assert lines[2].startswith(" N ") and all(len(c.strip().split(".")[1]) == 10 for c in lines[2].split()[1:])
+    f = tmp_path / "Output4.xyz"
+    f.write_text(text)
+    system2, xyz2 = read_input(str(f), dbase)                       # the reference strips "Energy: ... Kcal/mole"
+    assert system2.n_mol == system.n_mol and np.max(np.abs(xyz2 - xyz)) <= 5.1e-11
+    assert format_movie_frame(system, xyz, 1.5).split("\n")[1] == "Energy: 1.5 Kcal/mole"
+
+
+def test_coordinate_columns():
+    from transrot_b200.writers import _coord
+
+    assert _coord(1.909373313536205) == "     1.9093733135"
+    assert _coord(-12.5) == "   -12.5000000000"
+    assert _coord(123.25) == "   123.2500000000"
+    assert _coord(2.0e-4) == "     2.0E-4000000"        # the reference splits Double.toString on "." (Space.java:582): kept as is
+
+
+def test_acceptance_and_heat_capacity_lines():
+    assert format_acceptance_line(8888.888888888889, 12345, 20000) == "8888.89 0.61725\n"
+    assert format_acceptance_line(1.1368683772161603e-12, 1, 3) == "0.00 0.33333\n"
+    assert format_heat_capacity_line(1.1368683772161603e-12, -10.0, 5.0, 100) is None      # the `continue` of Main.java:228
+    line = format_heat_capacity_line(300.0, -2000.0, 40010.0, 100)
+    t, avg, cv = line.strip().split("\t")
+    assert t == "300.0" and avg == "-20.0" and float(cv) == pytest.approx((400.1 - 400.0) / (0.0019872 * 300.0 ** 2))
