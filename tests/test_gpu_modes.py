@@ -288,3 +288,25 @@ def test_two_gpu_sharding_is_invisible_per_chain(dbase, sample_cfg):
     assert whole[0].tobytes() == np.concatenate([a[0], b[0]]).tobytes()
     assert np.array_equal(whole[1], np.concatenate([a[1], b[1]]))
     assert whole[2].tobytes() == np.concatenate([a[2], b[2]]).tobytes()
+
+
+def test_error_convention_through_the_abi(dbase, sample_cfg):
+    """Non-zero status + tr_last_error text instead of exceptions across the ABI; the host turns them into the
+    RuntimeException("Error: ...") the reference would have thrown (Main.java:85-87)."""
+    from transrot_b200 import TransRotError
+
+    with Engine(0) as e:
+        with pytest.raises(TransRotError, match="Error: .*tr_init_chains"):
+            e.run(0)                                             # no chains yet
+        cfg = workload_config(sample_cfg, "h2o20")
+        e.set_system(system_from_config(dbase, cfg))
+        with pytest.raises(TransRotError, match="Error: .*tr_set_schedules"):
+            e.init_chains_seeded([1], cfg.spaceLen, cfg.maxPropFailures)
+        e.set_schedules(cfg)
+        with pytest.raises(TransRotError, match="threads_per_chain"):
+            e.set_options(threads_per_chain=48)
+        big = sample_cfg.copy(particles=[("H2O", 600)], spaceLen=40.0)          # 1800 sites > TR_MAX_SITES
+        with pytest.raises(TransRotError, match="exceed the limit"):
+            e.set_system(system_from_config(dbase, big))
+    with pytest.raises(TransRotError, match="out of range"):
+        Engine(99)
