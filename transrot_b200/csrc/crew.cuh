@@ -154,7 +154,9 @@ struct CrewTables {
         return b + 16;
     }
 
-    __device__ static __forceinline__ int &alive(unsigned char *smem) { return *(int *)smem; }
+    // "some chain still has work" for round r, written by the control warp one round ahead: two slots by round
+    // parity, so the warps that read it at the top of round r never race with the write for round r + 1
+    __device__ static __forceinline__ int &alive(unsigned char *smem, int round) { return ((int *)smem)[round & 1]; }
     __device__ static __forceinline__ int mol_off(const unsigned char *smem, int m) { return *(const int *)(smem + OFF_MOL_OFF + 4 * m); }
     __device__ static __forceinline__ int moveable(const unsigned char *smem, int i) { return *(const int *)(smem + OFF_MOVEABLE + 4 * i); }
     __device__ static __forceinline__ int site_pos(const unsigned char *smem, int i) { return *(const int *)(smem + OFF_SITE_POS + 4 * i); }
@@ -911,7 +913,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             } else if (mine) pl->mode = PLAN_IDLE;
             const unsigned any = __ballot_sync(0xffffffffu, mode != PLAN_IDLE || mode_cur != PLAN_IDLE);
             mode_prev = mode_cur; mode_cur = mode;
-            if (lane == 0) TL::alive(smem) = (int)any;
+            if (lane == 0) TL::alive(smem, r + 1) = (int)any;
             TM(const long long tm1 = clock64(); tm_a += tm1 - tm0; tm_rounds++;)
             crew_bar(NT);
             TM(tm_c += clock64() - tm1;)
@@ -940,7 +942,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
         int last_oob = 0;
         crew_bar(NT);                                       // plan[0] is written
         for (int r = 0;; r++) {
-            if (TL::alive(smem) == 0) break;
+            if (TL::alive(smem, r) == 0) break;
             TM(const long long tm0 = clock64(); tm_rounds++;)
             if (has) {
                 const CrewPlan *pl = &cs->plan[r & 1];
