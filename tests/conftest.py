@@ -12,6 +12,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """Build what is missing or stale (nvcc cross-compiles without a GPU): the CUDA library and the C oracle."""
+    from transrot_b200.build import build as build_cuda
+    from oracle.oracle import build as build_oracle
+
+    build_cuda()
+    build_oracle()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
