@@ -3,4 +3,6 @@ run() { # name lib args...
   TR_LIB=$lib timeout 120 python bench.py --steps 3 --warmup 1 --moves-per-point 1000 --no-cpu-baseline "$@" 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', d['config']['chains_per_gpu'], round(d['value']/1e9,4), round(d['ms_per_step'],2))"
 }
 run base transrot_b200/libtransrot_b200.so
-run prefetch exp_libs/lib_pf.so
+run ctrl+1000 exp_libs/lib_sc1000.so
+run ctrl+2000 exp_libs/lib_sc2000.so
+run e+500 exp_libs/lib_se500.so
