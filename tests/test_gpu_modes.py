@@ -310,3 +310,24 @@ def test_error_convention_through_the_abi(dbase, sample_cfg):
             e.set_system(system_from_config(dbase, big))
     with pytest.raises(TransRotError, match="out of range"):
         Engine(99)
+
+
+@pytest.mark.parametrize("tpc", [0, 16])
+def test_degenerate_schedules(engine, dbase, sample_cfg, tpc):
+    """Points per Tooth = 1 makes delT = t / 0 = Infinity (and 0 / 0 = NaN in the finale, where every uphill move is
+    then accepted: SURVEY Q11); Moves per Point = 1 makes every move the last of its point."""
+    cases = [
+        workload_config(sample_cfg, "sample8", movePerPt=40, ptsPerTooth=1, numTeeth=3, finale=True, maxTemp=500.0),
+        workload_config(sample_cfg, "sample8", movePerPt=1, ptsPerTooth=7, ptsAddedPerTooth=3, numTeeth=4, maxTemp=900.0),
+        workload_config(sample_cfg, "h2o20", movePerPt=2, ptsPerTooth=2, numTeeth=2, finale=True, writeConfHeatCapacitiesEnabled=True),
+    ]
+    for cfg in cases:
+        seeds = [61, 62, 63]
+        n = cfg.total_moves()
+        engine.set_system(system_from_config(dbase, cfg))
+        engine.set_schedules(cfg)
+        engine.set_options(trace_moves=n, threads_per_chain=tpc)
+        engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+        engine.run(0)
+        _check_records(engine, dbase, cfg, seeds, trace_moves=n)
+    engine.set_options(trace_moves=0, threads_per_chain=0)
