@@ -327,7 +327,9 @@ def run_ours(args):
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                "bound": "fp64", "bound_note": "FP64 pipe: the path is neither HBM- nor tensor-bound (chain state stays on chip, "
+                                               "no contraction); achieved = executed site-pair evaluations x 19 flop / kernel time",
+                "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved_tflops / peak_tflops, "traffic": None,
                 "kernel": "crew_kernel" if (args.threads_per_chain == 0 and system.n_sites <= 64) else "anneal_kernel",
                 "flops_per_pair_eval": FLOPS_PER_PAIR,
