@@ -331,3 +331,29 @@ def test_degenerate_schedules(engine, dbase, sample_cfg, tpc):
         engine.run(0)
         _check_records(engine, dbase, cfg, seeds, trace_moves=n)
     engine.set_options(trace_moves=0, threads_per_chain=0)
+
+
+def test_long_run_decisions_identical(engine, dbase, sample_cfg):
+    """The stated number of initial steps: 200 000 moves of the shipped sawtooth shape on (H2O)20 with every decision
+    identical to the oracle (tools/long_parity.py: 1 000 000 moves, three seeds, also identical).  Trial geometries
+    use CUDA's sin/cos instead of glibc's, so coordinates - and with them the energies - drift apart at the 1e-11
+    level over such a run; the final minima still agree to 1e-12."""
+    cfg = workload_config(sample_cfg, "h2o20", movePerPt=5000)
+    n = cfg.total_moves()
+    seeds = [1000, 1001]
+    engine.set_system(system_from_config(dbase, cfg))
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=n)
+    engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+    engine.run(0)
+    tr, mins = engine.trace(), engine.pack_minima()
+    for i, seed in enumerate(seeds):
+        sp = oracle_start(dbase, cfg, seed)
+        e0 = sp.write_snapshot(0)
+        res = sp.sawtooth_anneal(e0, trace_cap=n, snap_cap=8)
+        first, _, err_cond = compare_traces(tr[i], res.trace, res.trace_abs)
+        assert first == -1, f"seed {seed}: decisions diverge at move {first} of {n}"
+        assert err_cond <= 1e-10
+        emin, tmin = sp.min_energy()
+        assert mins["tooth"][i] == tmin and abs(mins["energy"][i] - emin) <= 1e-12 * abs(emin)
+    engine.set_options(trace_moves=0)
