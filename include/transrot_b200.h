@@ -160,6 +160,9 @@ int  tr_set_schedules(tr_ctx *ctx, const tr_schedule *sched, int32_t n_sched);
  * <= 192 sites) or 128/256 (block per chain). */
 int  tr_set_options(tr_ctx *ctx, int64_t trace_moves, int32_t record_points,
                     int32_t record_snapshots, int32_t threads_per_chain);
+/* Keep the structure writeMovie appends after every point (Space.java:740-790), set before tr_init_*.  Off by
+ * default: one [S][3] frame per point and chain (needs record_points). */
+int  tr_set_record_movie(tr_ctx *ctx, int32_t on);
 
 /* Seeded start = Main.java:34-37 (seed fan-out) + Main.java:58-60 / Space.java:72-117
  * (propagate with box growth and the random initial rotation), all on the device.
@@ -191,6 +194,9 @@ int  tr_get_sites(tr_ctx *ctx, double *sites /* [n_chains][S][3] */, double *com
 int  tr_get_points(tr_ctx *ctx, tr_point_rec *out, int64_t cap_per_chain);
 int  tr_get_snapshots(tr_ctx *ctx, double *energy /* [n_chains][cap] */, int32_t *tooth /* same */,
                       double *sites /* [n_chains][cap][S][3] or NULL */, int64_t cap_per_chain);
+/* The movie frames: frame p of a chain belongs to its point record p (movie_written says whether the reference
+ * appended it, Main.java:228). */
+int  tr_get_movie(tr_ctx *ctx, double *sites /* [n_chains][cap][S][3] */, int64_t cap_per_chain);
 int  tr_get_trace(tr_ctx *ctx, tr_trace_rec *out /* [n_chains][trace_moves] */);
 int  tr_get_rng_state(tr_ctx *ctx, uint32_t *out /* [n_chains][3][625] */);
 /* Per-chain minimum over the write(n) snapshots (Space.java:614-617), packed on the device.

@@ -357,3 +357,43 @@ def test_long_run_decisions_identical(engine, dbase, sample_cfg):
         emin, tmin = sp.min_energy()
         assert mins["tooth"][i] == tmin and abs(mins["energy"][i] - emin) <= 1e-12 * abs(emin)
     engine.set_options(trace_moves=0)
+
+
+@pytest.mark.parametrize("tpc", [0, 32])
+def test_movie_frames(engine, dbase, sample_cfg, tpc):
+    """The structure Space.writeMovie appends after every point (Space.java:740-790): its energy is the point record's
+    movie_energy, the last frame of a tooth is the write(x+1) structure, skipped frames (Main.java:228) stay empty."""
+    from transrot_b200 import format_movie_frame
+
+    cfg = workload_config(sample_cfg, "sample8", movePerPt=400, ptsPerTooth=4, numTeeth=2, finale=True,
+                          writeConfHeatCapacitiesEnabled=True, maxTemp=700.0)
+    system = system_from_config(dbase, cfg)
+    seeds = [11, 12, 13]
+    engine.set_system(system)
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=0, threads_per_chain=tpc)
+    engine.set_record_movie(True)
+    engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+    engine.run(0)
+    pts, frames = engine.points(), engine.movie()
+    se, st, sx = engine.snapshots()
+    summ = engine.summary()
+    for i, seed in enumerate(seeds):
+        n = int(summ["points"][i])
+        p = pts[i, :n]
+        written = p["movie_written"] == 1
+        assert written.any() and (~written).any()
+        e = engine.total_energy(frames[i, :n][written])
+        assert np.max(rel_err(e, p["movie_energy"][written])) <= 1e-12
+        assert not frames[i, :n][~written].any()
+        # last point of tooth 0 (not the finale): the structure write(1) saw
+        last0 = int(np.nonzero((p["tooth"] == 0) & (p["finale"] == 0))[0][-1])
+        if written[last0]:
+            assert np.array_equal(frames[i, last0], sx[i, 1])
+        sp = oracle_start(dbase, cfg, seed)
+        res = sp.sawtooth_anneal(sp.write_snapshot(0), points_cap=n + 2, snap_cap=4)
+        assert np.max(rel_err(p["movie_energy"][written], res.points["movieEnergy"][written])) <= 1e-10
+    text = format_movie_frame(system, frames[0, 0], float(pts[0, 0]["movie_energy"]))
+    assert text.split("\n")[0].strip() == "24" and text.count("\n") == 2 + 24
+    engine.set_record_movie(False)
+    engine.set_options(trace_moves=0, threads_per_chain=0)

@@ -457,6 +457,9 @@ __device__ __noinline__ bool end_of_point(const KParams &P, unsigned char *smem,
         }
         double me = __longlong_as_double(0x7ff8000000000000LL);
         if (movie && P.points) me = team_total_energy<L, W, SPL, HAS_EXP>(smem, cs, P.sys, tid, warp, lane, mask);
+        if (movie && P.movie_sites && pi < P.max_points)          // the frame writeMovie appends (Space.java:740-790)
+            sites_to_global<Lay::TPC, Lay::NPOS>(Lay::sites(cs), P.movie_sites + ((size_t)chain * P.max_points + pi) * (size_t)P.sys.n_sites * 3,
+                                                 P.sys, tid);
         if (tid == 0) {
             if (P.points && pi < P.max_points) {
                 tr_point_rec r;

@@ -68,6 +68,8 @@ struct __align__(16) CrewPlan {
     int flags;                     // PF_*
     int refill;                    // stream whose ring gets the next window, 3 = none
     int snap_slot;                 // PLAN_TOTAL: write(n) slot to dump the structure into, or -1
+    int movie_slot;                // PLAN_TOTAL: point whose movie frame is dumped, or -1
+    int pad_[3];
 };
 
 struct __align__(16) CrewResult {  // what a team reports for the move it evaluated
@@ -536,7 +538,7 @@ __device__ __noinline__ void crew_finish_point(const KParams &P, CrewChain *cs, 
 
 // Does the point that just ended need Space.calcEnergy (movie frame energy or write(x+1))?  Returns the
 // dump slot for the energy team in `snap_slot`.
-__device__ __forceinline__ bool crew_point_needs_total(const KParams &P, CrewChain *cs, int &snap_slot)
+__device__ __forceinline__ bool crew_point_needs_total(const KParams &P, CrewChain *cs, int &snap_slot, int &movie_slot)
 {
     const ChainCtrl *c = &cs->ctrl;
     const tr_schedule &sch = cs->sch;
@@ -547,7 +549,8 @@ __device__ __forceinline__ bool crew_point_needs_total(const KParams &P, CrewCha
     const bool start_finale = tooth_end && (c->x == numTeeth - 1) && !c->isDoubleCycle && sch.finale;
     const bool snap = tooth_end && !start_finale;
     snap_slot = (snap && P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
-    return snap || (movie && P.points != nullptr);
+    movie_slot = (movie && P.movie_sites && c->n_points < P.max_points) ? c->n_points : -1;
+    return snap || (movie && P.points != nullptr) || movie_slot >= 0;
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------
@@ -846,7 +849,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                 metro_ok = false;
 
                 // ---------------------------------------------- plan round r + 1
-                int flags = 0, refill = 3, snap_slot = -1;
+                int flags = 0, refill = 3, snap_slot = -1, movie_slot = -1;
                 if (mode_cur == PLAN_AUTO || mode_cur == PLAN_MOVE) {
                     // a move is being evaluated now: draw what its Metropolis test will need and both possible successors;
                     // if all of that exists, the team may go on by itself
@@ -882,7 +885,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     } else if (!c->done && z >= mpp) {
                         // end of the point: with a calcEnergy round first when its result is needed
                         flush_hot();
-                        if (crew_point_needs_total(P, cs, snap_slot)) mode = PLAN_TOTAL;
+                        if (crew_point_needs_total(P, cs, snap_slot, movie_slot)) mode = PLAN_TOTAL;
                         else {
                             crew_finish_point(P, cs, chain, 0.0, false);
                             load_hot();
@@ -908,7 +911,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     if (c->done && mode == PLAN_IDLE) live = false;
                 }
                 // (PLAN_TOTAL / PLAN_SYNC running now: wait for it)
-                pl->mode = mode; pl->flags = flags; pl->refill = refill; pl->snap_slot = snap_slot;
+                pl->mode = mode; pl->flags = flags; pl->refill = refill; pl->snap_slot = snap_slot; pl->movie_slot = movie_slot;
                 refill_cur = refill;
             } else if (mine) pl->mode = PLAN_IDLE;
             const unsigned any = __ballot_sync(0xffffffffu, mode != PLAN_IDLE || mode_cur != PLAN_IDLE);
@@ -980,9 +983,11 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     } else if (mode == PLAN_TOTAL) {
                         const double e = crew_total_energy<L, SPL, HAS_EXP>(smem, v, sys, info, q, tl, mask);
                         if (tl == 0) cs->etot = e;
-                        const int k = pl->snap_slot;
+                        const int k = pl->snap_slot, mv = pl->movie_slot;
                         if (k >= 0)
                             crew_sites_to_global<L, SPL>(v, P.snap_sites + ((size_t)(chain0 + c) * P.max_snaps + k) * (size_t)sys.n_sites * 3, sys, tl);
+                        if (mv >= 0)
+                            crew_sites_to_global<L, SPL>(v, P.movie_sites + ((size_t)(chain0 + c) * P.max_points + mv) * (size_t)sys.n_sites * 3, sys, tl);
                     }
                     TM(const long long tm2 = clock64(); tm_a += tm2 - tm1;)
                     crew_ring_end<L>(cs, w, tl, mask);

@@ -72,6 +72,7 @@ struct KParams {
     double *snap_energy;        // [n_chains][max_snaps]
     int *snap_tooth;            // [n_chains][max_snaps]
     double *snap_sites;         // [n_chains][max_snaps][S][3] or null
+    double *movie_sites;        // [n_chains][max_points][S][3] or null
     tr_trace_rec *trace;        // [n_chains][trace_moves] or null
     long long n_chains;
     long long max_moves;        // <= 0: run to completion

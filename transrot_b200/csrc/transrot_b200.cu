@@ -77,12 +77,12 @@ struct tr_ctx {
 
     // options
     long long trace_moves = 0;
-    int record_points = 1, record_snapshots = 1, threads_per_chain = 0;
+    int record_points = 1, record_snapshots = 1, threads_per_chain = 0, record_movie = 0;
 
     // chains
     long long n_chains = 0, first_chain = 0;
     DevBuf<ChainCtrl> d_ctrl;
-    DevBuf<double> d_sites, d_com, d_snap_energy, d_snap_sites;
+    DevBuf<double> d_sites, d_com, d_snap_energy, d_snap_sites, d_movie_sites;
     DevBuf<uint32_t> d_mt;
     DevBuf<int> d_snap_tooth;
     DevBuf<tr_point_rec> d_points;
@@ -438,6 +438,10 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
     CK(ctx, ctx->d_snap_tooth.alloc(C * max_snaps));
     CK(ctx, cudaMemsetAsync(ctx->d_snap_tooth.p, 0xff, C * max_snaps * sizeof(int), ctx->stream));
     if (ctx->record_snapshots) CK(ctx, ctx->d_snap_sites.alloc(C * max_snaps * S * 3)); else ctx->d_snap_sites.release();
+    if (ctx->record_movie && ctx->record_points) {
+        CK(ctx, ctx->d_movie_sites.alloc(C * (size_t)max_points * S * 3));
+        CK(ctx, cudaMemsetAsync(ctx->d_movie_sites.p, 0, C * (size_t)max_points * S * 3 * sizeof(double), ctx->stream));
+    } else ctx->d_movie_sites.release();
     if (ctx->record_points) {
         CK(ctx, ctx->d_points.alloc(C * max_points));
         CK(ctx, cudaMemsetAsync(ctx->d_points.p, 0, C * max_points * sizeof(tr_point_rec), ctx->stream));
@@ -660,6 +664,13 @@ extern "C" int tr_set_options(tr_ctx *ctx, int64_t trace_moves, int32_t record_p
     return TR_OK;
 }
 
+extern "C" int tr_set_record_movie(tr_ctx *ctx, int32_t on)
+{
+    if (!ctx) return TR_EINVAL;
+    ctx->record_movie = on ? 1 : 0;
+    return TR_OK;
+}
+
 extern "C" int tr_init_chains_seeded(tr_ctx *ctx, int64_t n_chains, int64_t first_chain, const int64_t *seeds,
                                      const int32_t *sched_idx, double space_len, int32_t max_prop_failures)
 {
@@ -756,6 +767,7 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     P.snap_energy = ctx->d_snap_energy.p;
     P.snap_tooth = ctx->d_snap_tooth.p;
     P.snap_sites = ctx->d_snap_sites.p;
+    P.movie_sites = ctx->d_movie_sites.p;
     P.trace = ctx->d_trace.p;
     P.n_chains = ctx->n_chains;
     P.max_moves = max_moves;
@@ -867,6 +879,22 @@ extern "C" int tr_get_snapshots(tr_ctx *ctx, double *energy, int32_t *tooth, dou
         const size_t row = (size_t)ctx->sys.n_sites * 24;
         CK(ctx, cudaMemcpy2DAsync(sites, cap * row, ctx->d_snap_sites.p, K * row, K * row, C, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return TR_OK;
+}
+
+extern "C" int tr_get_movie(tr_ctx *ctx, double *sites, int64_t cap_per_chain)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, sites != nullptr, "Error: tr_get_movie: sites is NULL");
+    NEED(ctx, ctx->d_movie_sites.p != nullptr, "Error: movie frames were not recorded (tr_set_record_movie before tr_init_chains_*)");
+    NEED(ctx, cap_per_chain >= ctx->max_points, "Error: tr_get_movie: buffer holds %lld frames per chain, %d needed",
+         (long long)cap_per_chain, ctx->max_points);
+    const size_t C = (size_t)ctx->n_chains, K = (size_t)ctx->max_points, cap = (size_t)cap_per_chain;
+    const size_t row = (size_t)ctx->sys.n_sites * 3 * sizeof(double);
+    CK(ctx, cudaMemcpy2DAsync(sites, cap * row, ctx->d_movie_sites.p, K * row, K * row, C, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return TR_OK;
 }

@@ -81,6 +81,8 @@ _SIGNATURES = {
     "tr_get_sites": [C.c_void_p, C.c_void_p, C.c_void_p],
     "tr_get_points": [C.c_void_p, C.c_void_p, C.c_int64],
     "tr_get_snapshots": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64],
+    "tr_set_record_movie": [C.c_void_p, C.c_int32],
+    "tr_get_movie": [C.c_void_p, C.c_void_p, C.c_int64],
     "tr_get_trace": [C.c_void_p, C.c_void_p],
     "tr_get_rng_state": [C.c_void_p, C.c_void_p],
     "tr_pack_minima": [C.c_void_p, C.c_void_p, C.c_void_p],
@@ -276,6 +278,17 @@ class Engine:
         x = np.zeros((self.n_chains, cap, self.system.n_sites, 3), dtype=np.float64) if with_sites else None
         self._ck(self.L.tr_get_snapshots(self.h, e.ctypes.data, t.ctypes.data, _ptr(x), cap))
         return e, t, x
+
+    def set_record_movie(self, on: bool = True):
+        """Keep the structure Space.writeMovie appends after every point (before init_chains_*)."""
+        self._ck(self.L.tr_set_record_movie(self.h, int(bool(on))))
+
+    def movie(self) -> np.ndarray:
+        """[n_chains, points, S, 3]: frame p belongs to point record p."""
+        cap, _ = self.max_points()
+        out = np.zeros((self.n_chains, cap, self.system.n_sites, 3), dtype=np.float64)
+        self._ck(self.L.tr_get_movie(self.h, out.ctypes.data, cap))
+        return out
 
     def trace(self) -> np.ndarray:
         out = np.zeros((self.n_chains, self.trace_moves), dtype=TRACE_DTYPE)
