@@ -397,3 +397,45 @@ def test_movie_frames(engine, dbase, sample_cfg, tpc):
     assert text.split("\n")[0].strip() == "24" and text.count("\n") == 2 + 24
     engine.set_record_movie(False)
     engine.set_options(trace_moves=0, threads_per_chain=0)
+
+
+def test_replayed_output_directory(engine, dbase, sample_cfg, tmp_path):
+    """Device buffers -> the reference's output directory (Output0..N.xyz, movies, acceptance ratios, minimum copy);
+    every OutputN.xyz restarts through read_input and reproduces its header energy on the device."""
+    from transrot_b200 import replay_outputs
+
+    cfg = workload_config(sample_cfg, "sample8", movePerPt=300, ptsPerTooth=3, numTeeth=3, writeAcceptanceRatios=True)
+    system = system_from_config(dbase, cfg)
+    engine.set_system(system)
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=0)
+    engine.set_record_movie(True)
+    engine.init_chains_seeded([42], cfg.spaceLen, cfg.maxPropFailures)
+    engine.run(0)
+    n = int(engine.summary()["points"][0])
+    se, st, sx = engine.snapshots()
+    mins = engine.pack_minima()
+    out = tmp_path / "run"
+    replay_outputs(str(out), system, cfg, engine.points()[0, :n], se[0], st[0], sx[0], engine.movie()[0], int(mins["tooth"][0]))
+    names = sorted(os.listdir(out))
+    assert [f"Output{k}.xyz" for k in range(4)] == [x for x in names if x.startswith("Output") and "_" not in x]
+    assert {"Output0_1_Movie.xyz", "Output1_2_Movie.xyz", "Output2_3_Movie.xyz", "acceptance_ratios.txt"} <= set(names)
+    assert f"Min_Energy_Structure_{int(mins['tooth'][0])}.xyz" in names
+    assert len(open(out / "acceptance_ratios.txt").read().splitlines()) == 9
+    # the shipped annealing block has heat capacities on: the t = 0 point of each tooth hits the `continue` of
+    # Main.java:228 (no heat-capacity line, no movie frame)
+    assert cfg.writeConfHeatCapacitiesEnabled
+    assert open(out / "Output0_1_Movie.xyz").read().count("Energy:") == 2
+    assert len(open(out / "configurational_heat_capacities.txt").read().splitlines()) == 6
+    for k in range(4):
+        sys_k, xyz = read_input(str(out / f"Output{k}.xyz"), dbase)
+        header = float(open(out / f"Output{k}.xyz").read().split("\n")[1].split()[1])
+        # reference quirk kept: Double.toString switches to "4.37E-4" below 1e-3 and Space.write splits it on "."
+        # (Space.java:582-591), so such a coordinate is written as "4.371995E-40" and restarts as ~0
+        tiny = np.abs(sx[0, k]) < 1e-3
+        assert header == se[0, k] and np.max(np.abs(xyz - sx[0, k])[~tiny]) <= 5.1e-11 and np.all(np.abs(xyz[tiny]) < 1e-30)
+        # the file rounds coordinates to 10 decimals: the restart energy moves by ~1e-8 relative at most
+        if not tiny.any():
+            assert abs(engine.total_energy(xyz[None])[0] - header) <= 1e-7 * abs(header)
+    engine.set_system(system)
+    engine.set_record_movie(False)

@@ -12,6 +12,7 @@ from .engine import (  # noqa: F401
     load_library, schedule_from_config,
 )
 from .sharding import chain_range, gather_minima, global_minimum, owner_of  # noqa: F401
+from .replay import replay_outputs  # noqa: F401
 from .writers import (  # noqa: F401
     format_acceptance_line, format_energies, format_heat_capacity_line, format_movie_frame, format_output_xyz,
     java_double_to_string, precision_round,
