@@ -59,3 +59,31 @@ def test_acceptance_and_heat_capacity_lines():
     line = format_heat_capacity_line(300.0, -2000.0, 40010.0, 100)
     t, avg, cv = line.strip().split("\t")
     assert t == "300.0" and avg == "-20.0" and float(cv) == pytest.approx((400.1 - 400.0) / (0.0019872 * 300.0 ** 2))
+
+
+def test_replay_outputs_from_synthetic_buffers(dbase, sample_cfg, golden_dir, tmp_path):
+    """The output directory is rebuilt from plain arrays: no device needed to exercise the host side of the seam."""
+    from transrot_b200 import POINT_DTYPE, replay_outputs
+
+    system, xyz = read_input(os.path.join(golden_dir, "sample8.input.xyz"), dbase)
+    cfg = sample_cfg.copy(movePerPt=10, ptsPerTooth=2, numTeeth=2, writeAcceptanceRatios=True, writeConfHeatCapacitiesEnabled=True)
+    pts = np.zeros(4, dtype=POINT_DTYPE)
+    pts["tooth"] = [0, 0, 1, 1]
+    pts["point"] = [0, 1, 0, 1]
+    pts["temp"] = [100.0, 0.0, 80.0, 0.0]
+    pts["accepted"] = [4, 9, 5, 8]
+    pts["total"] = [10, 20, 10, 20]
+    pts["movie_written"] = [1, 0, 1, 0]                # the t = 0 points hit the `continue` of Main.java:228
+    pts["total_energy"] = [-4000.0, -4100.0, -4200.0, -4300.0]
+    pts["total_squared_energy"] = [1600400.0, 1681000.0, 1764400.0, 1849000.0]
+    pts["movie_energy"] = [-400.5, np.nan, -420.25, np.nan]
+    movie = np.stack([xyz + 0.01 * i for i in range(4)])
+    out = tmp_path / "job"
+    replay_outputs(str(out), system, cfg, pts, np.array([-390.0, -410.0, -430.0]), np.array([0, 1, 2]), np.stack([xyz, xyz + 0.1, xyz + 0.2]),
+                   movie, min_tooth=2)
+    assert sorted(os.listdir(out)) == ["Min_Energy_Structure_2.xyz", "Output0.xyz", "Output0_1_Movie.xyz", "Output1.xyz", "Output1_2_Movie.xyz",
+                                      "Output2.xyz", "acceptance_ratios.txt", "configurational_heat_capacities.txt"]
+    assert open(out / "acceptance_ratios.txt").read() == "100.00 0.40000\n0.00 0.45000\n80.00 0.50000\n0.00 0.40000\n"
+    assert len(open(out / "configurational_heat_capacities.txt").read().splitlines()) == 2
+    assert open(out / "Min_Energy_Structure_2.xyz").read() == open(out / "Output2.xyz").read()
+    assert open(out / "Output0_1_Movie.xyz").read().split("\n")[1] == "Energy: -400.5 Kcal/mole"
