@@ -401,9 +401,9 @@ __device__ __forceinline__ void crew_move(const unsigned char *smem, const CrewV
     double eS = 0.0, eE = 0.0;
     for (int a = 0; a < sm; a++) {
         const StageSite st = v.stage[a];
-        if (HAS_EXP) stage_site_energy<SPL, SPL, 2>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
-        else if (LJS > 0 && st.lj) stage_site_energy<SPL, LJS, 1>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
-        else stage_site_energy<SPL, 0, 0>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
+        if (HAS_EXP) stage_site_energy<SPL, SPL, 2, false>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
+        else if (LJS > 0 && st.lj) stage_site_energy<SPL, LJS, 1, false>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
+        else stage_site_energy<SPL, 0, 0, false>(st, tab_cd, tab_ab, x, y, z, qm, col, eS, eE);
     }
     [[maybe_unused]] const long long tq2 = TMCLK();
     TMG(1, tq2 - tq1);
