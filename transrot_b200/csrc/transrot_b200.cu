@@ -30,6 +30,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
     cudaError_t alloc(size_t count)
     {
+        if (p && n == count) return cudaSuccess;      // same batch shape as last time: keep the allocation
         release();
         if (count == 0) return cudaSuccess;
         cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
