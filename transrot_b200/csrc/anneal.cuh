@@ -296,23 +296,23 @@ __device__ __forceinline__ void stage_site_energy(const StageSite &st, const uns
                                                   const double (&x)[SPL], const double (&y)[SPL], const double (&z)[SPL],
                                                   const double (&qm)[SPL], const int (&col)[SPL], double &eS, double &eE)
 {
-    if (!PAIRS) {
+    if constexpr (!PAIRS) {
 #pragma unroll
         for (int k = 0; k < SPL; k++) {
             if (k < LJN) group_energy<1, 1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
             else group_energy<1, 0, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int k = 0; k < SPL; k += 2) {
-        if (k + 1 < SPL) {
-            if (k + 1 < LJN) group_energy<2, 2, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
-            else if (k < LJN) group_energy<2, 1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
-            else group_energy<2, 0, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
-        } else {
-            if (k < LJN) group_energy<1, 1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
-            else group_energy<1, 0, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+        for (int k = 0; k < SPL; k += 2) {
+            if (k + 1 < SPL) {
+                if (k + 1 < LJN) group_energy<2, 2, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+                else if (k < LJN) group_energy<2, 1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+                else group_energy<2, 0, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            } else {
+                if (k < LJN) group_energy<1, 1, MODE_LJ>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+                else group_energy<1, 0, 0>(st, tab_cd, tab_ab, x + k, y + k, z + k, qm + k, col + k, eS, eE);
+            }
         }
     }
 }
