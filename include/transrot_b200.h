@@ -39,6 +39,12 @@ extern "C" {
 #define TR_ECUDA      -3   /* a CUDA runtime call or kernel failed              */
 #define TR_ELIMIT     -4   /* system exceeds a compiled-in limit (see below)    */
 #define TR_ENOMEM     -5
+#define TR_ERNG       -6   /* a chain was abandoned: its random-stream ring could not be refilled (tr_get_summary) */
+#define TR_ENCCL      -7   /* NCCL could not be loaded or a collective failed (tr_*_multi)                        */
+
+#define TR_KERNEL_AUTO 0   /* tr_set_kernel: let the library choose                                          */
+#define TR_KERNEL_TEAM 1   /* team kernel (anneal.cuh): every lane of a chain's team runs the control flow   */
+#define TR_KERNEL_CREW 2   /* warp-specialised kernel (crew.cuh): control warps + energy teams                */
 
 #define TR_MAX_MOL_SITES  16    /* sites in one particle                        */
 #define TR_MAX_SITES      1536  /* sites in `space`                             */
@@ -164,6 +170,19 @@ int  tr_set_options(tr_ctx *ctx, int64_t trace_moves, int32_t record_points,
  * default: one [S][3] frame per point and chain (needs record_points). */
 int  tr_set_record_movie(tr_ctx *ctx, int32_t on);
 
+/* Kernel family and launch geometry, set before tr_init_* (0 / TR_KERNEL_AUTO = automatic).  For experiments and
+ * tests; the automatic choice is what bench.py times. */
+int  tr_set_kernel(tr_ctx *ctx, int32_t kernel, int32_t chains_per_block, int32_t blocks_per_sm);
+/* The kernel family and variant the live chain batch runs with, e.g. "crew_kernel<L=16,SPL=4>" ("" before tr_init_*). */
+const char *tr_kernel_name(const tr_ctx *ctx);
+/* sizeof / offsetof of the structs above as this library was compiled: {sizeof(tr_system), offsetof(mol_site_off),
+ * offsetof(pair_abcd), sizeof(tr_schedule), offsetof(moves_per_point), offsetof(write_conf_heat_capacities),
+ * sizeof(tr_point_rec), offsetof(temp), offsetof(movie_energy), sizeof(tr_trace_rec), offsetof(e_start),
+ * offsetof(running), sizeof(tr_chain_summary), offsetof(moves), offsetof(min_tooth), sizeof(tr_minimum),
+ * offsetof(chain), offsetof(tooth)}.  Returns the number of entries (18); fills out[] when cap is large enough.
+ * A binding checks its own layouts against these at load time. */
+int  tr_abi_sizes(int32_t *out, int32_t cap);
+
 /* Seeded start = Main.java:34-37 (seed fan-out) + Main.java:58-60 / Space.java:72-117
  * (propagate with box growth and the random initial rotation), all on the device.
  * sched_idx may be NULL (all chains use schedule 0).  first_chain only labels results. */
@@ -204,7 +223,42 @@ int  tr_get_rng_state(tr_ctx *ctx, uint32_t *out /* [n_chains][3][625] */);
 int  tr_pack_minima(tr_ctx *ctx, tr_minimum *host_out, void *device_out);
 /* The structure written by write(min_tooth) for one chain. */
 int  tr_get_min_structure(tr_ctx *ctx, int64_t chain, double *sites /* [S][3] */, double *energy, int32_t *tooth);
+/* The same structure for chains first .. first+count-1 (local indices), packed on the device: [count][S][3] (needs
+ * record_snapshots).  host_out and/or device_out (a device pointer, e.g. the send buffer of an NCCL all-gather of
+ * final structures). */
+int  tr_pack_min_structures(tr_ctx *ctx, int64_t first, int64_t count, double *host_out, void *device_out);
 int  tr_max_points(tr_ctx *ctx, int64_t *points_per_chain, int64_t *snapshots_per_chain);
+
+/* ---- multi-GPU: one host thread, all GPUs of a box (SURVEY.md §8b,e) -------------------------------
+ * The reference is one JVM with one thread (Main.java:17), so a Java host drives every GPU from one process: a
+ * tr_multi owns one tr_ctx per device plus an NCCL communicator over them (ncclCommInitAll; NCCL is bound at run
+ * time, and not at all for n == 1).  Chains are sharded in contiguous GLOBAL ranges (tr_multi_chain_range); seeds and
+ * parameter sets are indexed by the global chain id, so per-chain results do not depend on the number of devices.
+ * There is no traffic while the chains anneal.  tr_multi_ctx(m, i) gives the per-device context for every tr_get_* /
+ * probe call of this header (local chain j of device i is global chain first_chain + lo_i + j). */
+typedef struct tr_multi tr_multi;
+int  tr_create_multi(const int32_t *devices, int32_t n, tr_multi **out);
+void tr_destroy_multi(tr_multi *m);
+const char *tr_multi_last_error(const tr_multi *m);     /* m == NULL: last failing tr_create_multi */
+int32_t tr_multi_size(const tr_multi *m);
+tr_ctx *tr_multi_ctx(tr_multi *m, int32_t i);
+void tr_multi_chain_range(int32_t rank, int32_t world, int64_t n_total, int64_t *lo, int64_t *hi);
+int  tr_multi_set_system(tr_multi *m, const tr_system *sys);
+int  tr_multi_set_schedules(tr_multi *m, const tr_schedule *sched, int32_t n_sched);
+int  tr_multi_set_options(tr_multi *m, int64_t trace_moves, int32_t record_points, int32_t record_snapshots, int32_t threads_per_chain);
+/* seeds / sched_idx hold ALL n_chains entries; device i takes its range. */
+int  tr_multi_init_chains_seeded(tr_multi *m, int64_t n_chains, int64_t first_chain, const int64_t *seeds,
+                                 const int32_t *sched_idx, double space_len, int32_t max_prop_failures);
+int  tr_multi_run(tr_multi *m, int64_t max_moves);       /* every device, asynchronously */
+int  tr_multi_synchronize(tr_multi *m);
+int  tr_multi_last_run_ms(tr_multi *m, float *ms_max);   /* max over devices of tr_last_run_ms */
+/* The one exchange of the path (what Space.writeMinEnergy needs over all chains, Space.java:836-844): every device
+ * packs its chains' minima, an NCCL all-gather leaves all n_chains records on every device, each device finds the
+ * global winner (lowest energy, ties to the lowest chain id), and the owner broadcasts the winning structure.
+ * all: [n_chains] records ordered by global chain id, or NULL; best: the winner, or NULL; best_sites: [S][3], or NULL. */
+int  tr_gather_minima(tr_multi *m, tr_minimum *all, tr_minimum *best, double *best_sites);
+/* NCCL all-gather of EVERY chain's minimum structure: sites[n_chains][S][3] (BASELINE config #4). */
+int  tr_gather_min_structures(tr_multi *m, double *sites);
 
 /* ---- parity probes: Space.calcEnergy and the eStart/eEnd loop on supplied geometries ----- */
 int  tr_total_energy(tr_ctx *ctx, const double *sites /* [n][S][3] */, int64_t n, double *energy /* [n] */);

@@ -11,21 +11,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from oracle.oracle import OracleSpace, oracle_from_config  # noqa: E402
-from transrot_b200 import Config, system_from_config  # noqa: E402
-
-# BASELINE.json configs / SURVEY.md §8(d): particles and initial box
-WORKLOADS = {
-    "sample8": dict(particles=[("NH4+", 4), ("Cl-", 4)], spaceLen=5.0),
-    "h2o20": dict(particles=[("H2O", 20)], spaceLen=10.0),
-    "nh4cl32": dict(particles=[("NH4+", 32), ("Cl-", 32)], spaceLen=14.0),
-    "mixed64": dict(particles=[("NH4+", 16), ("Cl-", 16), ("H2O", 32)], spaceLen=14.0),
-    "h2o256": dict(particles=[("H2O", 256)], spaceLen=24.0),
-}
-
-
-def workload_config(base: Config, name: str, **kw) -> Config:
-    w = WORKLOADS[name]
-    return base.copy(particles=list(w["particles"]), spaceLen=w["spaceLen"], **kw)
+from transrot_b200 import Config, WORKLOADS, system_from_config, workload_config  # noqa: E402,F401
 
 
 def oracle_start(dbase, cfg: Config, seed: int, pair_table=None) -> OracleSpace:

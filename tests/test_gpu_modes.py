@@ -8,7 +8,7 @@ import pytest
 
 from helpers import compare_traces, oracle_start, rel_err, workload_config
 from oracle.oracle import JavaMT, OracleSpace
-from transrot_b200 import Config, Engine, read_dbase, read_input, system_from_config
+from transrot_b200 import Config, Engine, TR_KERNEL_AUTO, TR_KERNEL_CREW, read_dbase, read_input, system_from_config
 
 pytestmark = pytest.mark.gpu
 
@@ -240,13 +240,13 @@ def test_every_kernel_variant_takes_the_same_decisions(engine, dbase, sample_cfg
     system = system_from_config(dbase, cfg)
     ref = None
     for tpc in (0, "crew") + tuple(tpcs):
-        if tpc == "crew":                 # the warp-specialised kernel also where the automatic choice prefers a team kernel
-            os.environ["TR_FORCE_CREW"] = "1"
+        # "crew": the warp-specialised kernel also where the automatic choice prefers a team kernel
+        engine.set_kernel(TR_KERNEL_CREW if tpc == "crew" else TR_KERNEL_AUTO)
         engine.set_system(system)
         engine.set_schedules(cfg)
         engine.set_options(trace_moves=n, threads_per_chain=0 if tpc == "crew" else tpc)
         engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
-        os.environ.pop("TR_FORCE_CREW", None)
+        engine.set_kernel(TR_KERNEL_AUTO)
         engine.run(0)
         tr, mins = engine.trace(), engine.pack_minima()
         if ref is None:

@@ -113,11 +113,36 @@ def test_library_exports_every_declared_symbol():
     """The C-ABI library loads on a GPU-less host and exports everything include/transrot_b200.h declares."""
     assert os.path.exists(LIB_PATH), "libtransrot_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')"
     header = open(os.path.join(ROOT, "include", "transrot_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|void|const char \*)\s*\*?\s*(tr_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|void|int32_t|const char \*|tr_ctx \*)\s*\*?\s*(tr_[a-z0-9_]+)\s*\(", header, flags=re.M))
     assert declared == set(EXPORTED_SYMBOLS), declared ^ set(EXPORTED_SYMBOLS)
     lib = ctypes.CDLL(LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
+
+
+def test_binding_layouts_match_the_library():
+    """tr_abi_sizes: the struct layouts of the ctypes / numpy binding are checked against the library's own sizeof /
+    offsetof at load time (engine._check_abi) - no GPU needed."""
+    from transrot_b200 import load_library
+
+    L = load_library()
+    n = L.tr_abi_sizes(None, 0)
+    assert n == 18
+    buf = (ctypes.c_int32 * n)()
+    assert L.tr_abi_sizes(buf, n) == n
+    assert list(buf)[0] == 88 and list(buf)[3] == 88 and list(buf)[6] == 56 and list(buf)[9] == 64 and list(buf)[15] == 24
+
+
+def test_multi_chain_range_matches_the_python_sharding():
+    """tr_multi_chain_range (C) and sharding.chain_range (Python, used under torchrun) are the same partition."""
+    from transrot_b200 import load_library
+
+    L = load_library()
+    for n, world in [(4096, 8), (10, 3), (7, 7), (32768, 8), (5, 2)]:
+        for r in range(world):
+            lo, hi = ctypes.c_int64(), ctypes.c_int64()
+            L.tr_multi_chain_range(r, world, n, ctypes.byref(lo), ctypes.byref(hi))
+            assert (lo.value, hi.value) == chain_range(r, world, n)
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -87,3 +87,29 @@ def test_replay_outputs_from_synthetic_buffers(dbase, sample_cfg, golden_dir, tm
     assert len(open(out / "configurational_heat_capacities.txt").read().splitlines()) == 2
     assert open(out / "Min_Energy_Structure_2.xyz").read() == open(out / "Output2.xyz").read()
     assert open(out / "Output0_1_Movie.xyz").read().split("\n")[1] == "Energy: -400.5 Kcal/mole"
+
+
+def test_output_xyz_reproduces_the_reference_sample_byte_for_byte(dbase, golden_dir):
+    """The reference's src/Input.xyz (fixture sample8.input.xyz, byte-identical copy) is a sample of the very format
+    Space.write emits (Space.java:571-612): re-formatting its 24 atoms must give back its atom lines 3-26 exactly, and
+    the atom-count line."""
+    path = os.path.join(golden_dir, "sample8.input.xyz")
+    system, xyz = read_input(path, dbase)
+    want = open(path).read().split("\n")
+    got = format_output_xyz(system, xyz, -460.8203874165545).split("\n")
+    assert got[0] == want[0]
+    assert got[2:26] == want[2:26]
+    assert len([ln for ln in want[2:] if ln.strip()]) == 24
+    # the comment line: Space.write puts "Energy: ... Kcal/mole  " in front of the particle list readInput wants
+    assert got[1].endswith(want[1]) and got[1].startswith("Energy: ")
+
+
+def test_config_to_text_round_trips_through_the_parser(sample_cfg, tmp_path):
+    """Config.to_text writes a config.txt that Config.parseConfig (the reference's grammar, Config.java:36-48) reads back
+    to the same values: what tools/jvm_pin.sh feeds the JVM."""
+    from transrot_b200 import Config, workload_config
+
+    for cfg in (sample_cfg, workload_config(sample_cfg, "mixed64", staticTemp=True, maxTemp=0.00001, finale=True, eqConfigs=7)):
+        f = tmp_path / "config.txt"
+        f.write_text(cfg.to_text())
+        assert Config.parseConfig(str(f)) == cfg

@@ -331,6 +331,26 @@ __global__ void pack_minima_kernel(const ChainCtrl *ctrl, long long n_chains, lo
     out[i] = m;
 }
 
+// The structure write(min_tooth) saw, per chain: [n_chains][row] (what writeMinEnergy copies, Space.java:836-844).
+// The first snapshot with the lowest energy wins (strict < of Space.java:614).
+__global__ void pack_min_structures_kernel(const double *snap_energy, const int *snap_tooth, const double *snap_sites, long long n_chains,
+                                           int max_snaps, int row, double *out)
+{
+    const long long total = n_chains * row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long chain = i / row;
+        const int j = (int)(i % row);
+        int best = -1;
+        double eb = 0.0;
+        for (int k = 0; k < max_snaps; k++) {
+            if (snap_tooth[chain * max_snaps + k] < 0) continue;
+            const double e = snap_energy[chain * max_snaps + k];
+            if (best < 0 || e < eb) { best = k; eb = e; }
+        }
+        out[i] = best >= 0 ? snap_sites[((size_t)chain * max_snaps + best) * row + j] : __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
 __global__ void summary_kernel(const ChainCtrl *ctrl, long long n_chains, tr_chain_summary *out)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -12,89 +13,15 @@
 #include <vector>
 
 #include "../../include/transrot_b200.h"
+#include "context.cuh"
 #include "anneal.cuh"
-#include "crew.cuh"
 #include "setup_kernels.cuh"
 
 using namespace tr;
 
-namespace {
+namespace tr {
 
 thread_local std::string g_create_error;
-
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    cudaError_t alloc(size_t count)
-    {
-        if (p && n == count) return cudaSuccess;      // same batch shape as last time: keep the allocation
-        release();
-        if (count == 0) return cudaSuccess;
-        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
-    }
-};
-
-struct Variant { int L, W, SPL; int tpc() const { return W > 1 ? 32 * W : L; } };
-// (lanes per chain, warps per chain, sites per thread) instantiated below; capacity = tpc * SPL sites.
-// Order = preference of the automatic choice: half-warp teams while the cluster fits 64 sites, then a warp,
-// then a block per chain.
-const Variant kVariants[] = { {16, 1, 1}, {16, 1, 2}, {16, 1, 4}, {32, 1, 2}, {32, 1, 4}, {32, 1, 6},
-                              {32, 4, 6}, {32, 8, 3}, {32, 8, 6} };
-
-}  // namespace
-
-struct tr_ctx {
-    int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string err;
-    long long launches = 0;
-    bool have_run_time = false;
-    int sm_count = 0;
-    int max_smem_optin = 0;
-    int smem_per_sm = 0;
-
-    // system
-    bool have_system = false;
-    DevSystem sys{};
-    DevBuf<int> d_mol_off, d_site_info, d_moveable, d_site_ghost;
-    DevBuf<double> d_site_q, d_mol_radius, d_site_def, d_site_mass;
-    DevBuf<double2> d_pair_cd, d_pair_ab;
-    DevBuf<int> d_pos_site, d_site_pos, d_pos_info;
-    std::vector<int> h_site_info;
-    bool have_propagate_data = false;
-    std::vector<int> h_mol_off, h_site_lj;
-    Variant prepared{0, 0, 0};
-
-    // schedules
-    DevBuf<tr_schedule> d_sched;
-    std::vector<tr_schedule> h_sched;
-
-    // options
-    long long trace_moves = 0;
-    int record_points = 1, record_snapshots = 1, threads_per_chain = 0, record_movie = 0;
-
-    // chains
-    long long n_chains = 0, first_chain = 0;
-    DevBuf<ChainCtrl> d_ctrl;
-    DevBuf<double> d_sites, d_com, d_snap_energy, d_snap_sites, d_movie_sites;
-    DevBuf<uint32_t> d_mt;
-    DevBuf<int> d_snap_tooth;
-    DevBuf<tr_point_rec> d_points;
-    DevBuf<tr_trace_rec> d_trace;
-    int max_points = 0, max_snaps = 0;
-    Variant variant{16, 1, 1};
-    bool use_crew = false;        // warp-specialised kernel (crew.cuh): automatic choice while a chain fits one warp
-    int crew_chains = 0;          // chains per block, 0 = automatic
-};
-
-namespace {
 
 int fail(tr_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -107,17 +34,15 @@ int fail(tr_ctx *ctx, int code, const char *fmt, ...)
     return code;
 }
 
-#define CK(ctx, call)                                                                                   \
-    do {                                                                                                \
-        cudaError_t e__ = (call);                                                                       \
-        if (e__ != cudaSuccess)                                                                         \
-            return fail(ctx, TR_ECUDA, "Error: CUDA failure in %s: %s", #call, cudaGetErrorString(e__)); \
-    } while (0)
+}  // namespace tr
 
-#define NEED(ctx, cond, ...)                                \
-    do {                                                    \
-        if (!(cond)) return fail(ctx, TR_EINVAL, __VA_ARGS__); \
-    } while (0)
+namespace {
+
+// (lanes per chain, warps per chain, sites per thread) instantiated below; capacity = tpc * SPL sites.
+// Order = preference of the automatic choice: half-warp teams while the cluster fits 64 sites, then a warp,
+// then a block per chain.
+const Variant kVariants[] = { {16, 1, 1}, {16, 1, 2}, {16, 1, 4}, {32, 1, 2}, {32, 1, 4}, {32, 1, 6},
+                              {32, 4, 6}, {32, 8, 3}, {32, 8, 6} };
 
 template <typename T>
 int upload(tr_ctx *ctx, DevBuf<T> &buf, const T *src, size_t n)
@@ -252,117 +177,6 @@ cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol,
     return cudaGetLastError();
 }
 
-// ---- crew kernel (crew.cuh): launch geometry and dispatch ---------------------------------------
-
-#ifndef TR_CREW_EW
-#define TR_CREW_EW 7          // energy warps per block
-#endif
-#ifndef TR_CREW_MINB
-#define TR_CREW_MINB 2        // blocks per SM the register budget is squeezed for
-#endif
-#ifndef TR_CREW_BPS
-#define TR_CREW_BPS 2         // co-resident blocks per SM the chains-per-block choice aims at
-#endif
-
-int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
-template <int L, int SPL>
-void crew_sizes_t(const tr_ctx *ctx, int max_mol_sites, int *tables, int *stride)
-{
-    *tables = CrewTables<L, SPL>::table_bytes(ctx->sys.n_types, ctx->sys.has_exp != 0);
-    *stride = CrewTables<L, SPL>::chain_bytes(ctx->sys.n_mol, max_mol_sites);
-}
-
-int max_mol_sites_of(const tr_ctx *ctx)
-{
-    int m = 1;
-    for (size_t i = 0; i + 1 < ctx->h_mol_off.size(); i++) m = std::max(m, ctx->h_mol_off[i + 1] - ctx->h_mol_off[i]);
-    return m;
-}
-
-#define TR_CREW_CASES(CALL)                          \
-    switch (ctx->variant.L * 100 + ctx->variant.SPL) { \
-    case 1601: CALL(16, 1); break;                   \
-    case 1602: CALL(16, 2); break;                   \
-    case 1604: CALL(16, 4); break;                   \
-    case 3204: CALL(32, 4); break;                   \
-    case 3206: CALL(32, 6); break;                   \
-    default: return fail(ctx, TR_ELIMIT, "Error: no crew kernel for %d lanes x %d sites per lane", ctx->variant.L, ctx->variant.SPL); \
-    }
-
-// Chains per block C, bytes per chain region and dynamic shared memory of the crew kernel.  C is chosen so
-// that the grid fills every SM with TR_CREW_BPS co-resident blocks in ONE wave when the chains fit; with more
-// chains than that the grid simply runs in several waves.
-int crew_geometry(tr_ctx *ctx, long long n_chains, int *C, int *stride, int *smem)
-{
-    int tables = 0;
-    const int maxs = max_mol_sites_of(ctx);
-#define CALL_SIZES(L, SPL) crew_sizes_t<L, SPL>(ctx, maxs, &tables, stride)
-    TR_CREW_CASES(CALL_SIZES)
-#undef CALL_SIZES
-    const int bps = std::max(1, env_int("TR_CREW_BPS", TR_CREW_BPS));
-    const int per_block = std::min(ctx->max_smem_optin, (ctx->smem_per_sm - 1024 * bps) / bps);
-    int c_fit = (per_block - tables) / *stride;
-    if (c_fit < 1) c_fit = (ctx->max_smem_optin - tables) / *stride;     // fewer co-resident blocks, but it runs
-    if (c_fit < 1)
-        return fail(ctx, TR_ELIMIT, "Error: one chain needs %d bytes of shared memory, device offers %d", tables + *stride,
-                    ctx->max_smem_optin);
-    const long long slots = (long long)ctx->sm_count * bps;
-    int c = (int)std::min<long long>((n_chains + slots - 1) / slots, 32);
-    c = std::max(1, std::min(c, c_fit));
-    const int forced = ctx->crew_chains > 0 ? ctx->crew_chains : env_int("TR_CREW_C", 0);
-    if (forced > 0) c = std::max(1, std::min(std::min(forced, 32), (ctx->max_smem_optin - tables) / *stride));
-    c = std::min(c, TR_CREW_EW * (32 / ctx->variant.L));          // every chain of a block has its own energy team
-    *C = c;
-    *smem = tables + c * *stride;
-    return TR_OK;
-}
-
-template <int L, int SPL, int LJS, bool HAS_EXP>
-cudaError_t launch_crew_lj(tr_ctx *ctx, const KParams &P, int C, int stride, int smem, int maxs)
-{
-    constexpr int EW = TR_CREW_EW;
-    const unsigned blocks = (unsigned)((P.n_chains + C - 1) / C);
-    cudaError_t e;
-    if (P.trace) {
-        auto kern = crew_kernel<L, SPL, SPL, HAS_EXP, true, EW, 1>;        // tracing: one generic variant
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-        kern<<<blocks, 32 * (1 + EW), smem, ctx->stream>>>(P, C, stride, maxs);
-    } else {
-        auto kern = crew_kernel<L, SPL, LJS, HAS_EXP, false, EW, TR_CREW_MINB>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-        kern<<<blocks, 32 * (1 + EW), smem, ctx->stream>>>(P, C, stride, maxs);
-    }
-    return cudaGetLastError();
-}
-
-template <int L, int SPL>
-cudaError_t launch_crew_t(tr_ctx *ctx, const KParams &P, int C, int stride, int smem, int maxs)
-{
-    constexpr int THIRD = (SPL + 2) / 3 < 1 ? 1 : (SPL + 2) / 3;
-    const int lj_slots = (P.sys.n_lj_pos + L - 1) / L;
-    if (P.sys.has_exp) return launch_crew_lj<L, SPL, SPL, true>(ctx, P, C, stride, smem, maxs);
-    if (lj_slots == 0) return launch_crew_lj<L, SPL, 0, false>(ctx, P, C, stride, smem, maxs);
-    if (lj_slots <= THIRD) return launch_crew_lj<L, SPL, THIRD, false>(ctx, P, C, stride, smem, maxs);
-    return launch_crew_lj<L, SPL, SPL, false>(ctx, P, C, stride, smem, maxs);
-}
-
-int launch_crew(tr_ctx *ctx, const KParams &P)
-{
-    int C = 0, stride = 0, smem = 0;
-    if (int r = crew_geometry(ctx, P.n_chains, &C, &stride, &smem)) return r;
-    const int maxs = max_mol_sites_of(ctx);
-    cudaError_t e = cudaErrorInvalidValue;
-#define CALL_CREW(L, SPL) e = launch_crew_t<L, SPL>(ctx, P, C, stride, smem, maxs)
-    TR_CREW_CASES(CALL_CREW)
-#undef CALL_CREW
-    if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: crew kernel launch failed: %s", cudaGetErrorString(e));
-    return TR_OK;
-}
 
 #define TR_DISPATCH_CASES(CALL, HE)                                   \
     switch (key__) {                                                  \
@@ -395,19 +209,26 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
     NEED(ctx, ctx->have_system, "Error: tr_set_system must be called before initialising chains");
     NEED(ctx, !ctx->h_sched.empty(), "Error: tr_set_schedules must be called before initialising chains");
     NEED(ctx, n_chains > 0, "Error: n_chains must be positive");
+    ctx->n_chains = 0;            // the batch only becomes live when its initialisation has completed (commit_chains)
     Variant v;
     if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v))
         return fail(ctx, TR_ELIMIT, "Error: %d sites do not fit %d threads per chain (limit %d sites)", ctx->sys.n_sites,
                     ctx->threads_per_chain, TR_MAX_SITES);
     ctx->variant = v;
     // the crew kernel wins while a chain fits a half-warp team (<= 64 sites: 1.3 vs 1.1 G moves/s on (H2O)20); for
-    // 65..192 sites the warp-per-chain team kernel is ahead (0.55 vs 0.45 G moves/s on (NH4Cl)32), TR_FORCE_CREW=1 overrides
-    ctx->use_crew = ctx->threads_per_chain == 0 && v.W == 1 && (v.L == 16 || env_int("TR_FORCE_CREW", 0) != 0);
+    // 65..192 sites the warp-per-chain team kernel is ahead (0.55 vs 0.45 G moves/s on (NH4Cl)32); tr_set_kernel overrides
+    ctx->use_crew = ctx->threads_per_chain == 0 && v.W == 1 && ctx->kernel_choice != TR_KERNEL_TEAM &&
+                    (v.L == 16 || ctx->kernel_choice == TR_KERNEL_CREW);
     if (int r = prepare_variant(ctx, v)) return r;
+    {
+        char nm[96];
+        if (ctx->use_crew) snprintf(nm, sizeof nm, "crew_kernel<L=%d,SPL=%d>", v.L, v.SPL);
+        else snprintf(nm, sizeof nm, "anneal_kernel<L=%d,W=%d,SPL=%d>", v.L, v.W, v.SPL);
+        ctx->kernel_name = nm;
+    }
     int smem = 0;
     if (ctx->use_crew) {
-        int C = 0, stride = 0;
-        if (int r = crew_geometry(ctx, n_chains, &C, &stride, &smem)) return r;
+        if (int r = crew_smem_bytes(ctx, n_chains, &smem)) return r;
     } else {
         cudaError_t e;
 #define CALL_SMEM(L, W, SPL, HE) smem_need_t<L, W, SPL, HE>(ctx, &smem)
@@ -451,8 +272,17 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
         CK(ctx, ctx->d_trace.alloc(C * (size_t)ctx->trace_moves));
         CK(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, C * (size_t)ctx->trace_moves * sizeof(tr_trace_rec), ctx->stream));
     } else ctx->d_trace.release();
-    ctx->n_chains = n_chains;
+    ctx->pending_chains = n_chains;
     ctx->first_chain = first_chain;
+    ctx->live_trace_moves = ctx->trace_moves;
+    return TR_OK;
+}
+
+// The initialisation kernels have run and every staging copy has completed: the batch is live.
+int commit_chains(tr_ctx *ctx)
+{
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_chains = ctx->pending_chains;
     return TR_OK;
 }
 
@@ -469,13 +299,13 @@ int launch_init(tr_ctx *ctx, const long long *d_seeds, const int *d_sched_idx, c
     ip.seeds = d_seeds;
     ip.sched_idx = d_sched_idx;
     ip.mt_pos = d_mt_pos;
-    ip.n_chains = ctx->n_chains;
+    ip.n_chains = ctx->pending_chains;
     ip.space_len = space_len;
     ip.max_prop_failures = max_prop_failures;
     ip.propagate = propagate;
     ip.n_sched = (int)ctx->h_sched.size();
     const int threads = 64;
-    const unsigned blocks = (unsigned)((ctx->n_chains + threads - 1) / threads);
+    const unsigned blocks = (unsigned)((ctx->pending_chains + threads - 1) / threads);
     init_chains_kernel<<<blocks, threads, 0, ctx->stream>>>(ip);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
@@ -590,8 +420,10 @@ extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
     std::vector<int> type_lj((size_t)s->n_types, 0);
     for (int t1 = 0; t1 < s->n_types; t1++)
         for (int t2 = 0; t2 < s->n_types; t2++) {
-            const double2 v = cd[(size_t)t1 * s->n_types + t2];
-            if (!(v.x == 0.0) || !(v.y == 0.0) || has_exp) type_lj[(size_t)t1] = 1;
+            // row OR column: the ABI accepts tables that are not symmetric, and a site's class decides both how it is
+            // evaluated when staged (row) and which slot it occupies as "the other site" (column)
+            const double2 v = cd[(size_t)t1 * s->n_types + t2], w = cd[(size_t)t2 * s->n_types + t1];
+            if (!(v.x == 0.0) || !(v.y == 0.0) || !(w.x == 0.0) || !(w.y == 0.0) || has_exp) type_lj[(size_t)t1] = 1;
         }
     ctx->h_site_lj.assign((size_t)s->n_sites, 0);
     for (int i = 0; i < s->n_sites; i++) {
@@ -682,17 +514,16 @@ extern "C" int tr_init_chains_seeded(tr_ctx *ctx, int64_t n_chains, int64_t firs
          "Error: a seeded start needs mol_radius and site_def in tr_set_system (Space.propagate places particles)");
     NEED(ctx, space_len > 0.0, "Error: Length of Cubic Space must be positive");
     if (int r = alloc_chain_buffers(ctx, n_chains, first_chain)) return r;
-    DevBuf<long long> d_seeds;
-    DevBuf<int> d_idx;
+    DevBuf<long long> &d_seeds = ctx->d_seeds;
+    DevBuf<int> &d_idx = ctx->d_sched_idx;
     CK(ctx, d_seeds.alloc((size_t)n_chains));
     CK(ctx, cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_chains * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (sched_idx) {
         CK(ctx, d_idx.alloc((size_t)n_chains));
         CK(ctx, cudaMemcpyAsync(d_idx.p, sched_idx, (size_t)n_chains * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (int r = launch_init(ctx, d_seeds.p, d_idx.p, nullptr, space_len, max_prop_failures, 1)) return r;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return TR_OK;
+    if (int r = launch_init(ctx, d_seeds.p, sched_idx ? d_idx.p : nullptr, nullptr, space_len, max_prop_failures, 1)) return r;
+    return commit_chains(ctx);
 }
 
 extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t first_chain, const double *sites, int64_t n_structs,
@@ -704,6 +535,11 @@ extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t fi
     NEED(ctx, n_structs == 1 || n_structs == n_chains, "Error: n_structs must be 1 or n_chains");
     NEED(ctx, seeds != nullptr || mt_state != nullptr, "Error: give seeds or explicit RNG states");
     NEED(ctx, space_len > 0.0, "Error: Length of Cubic Space must be positive");
+    NEED(ctx, n_chains > 0, "Error: n_chains must be positive");
+    if (mt_state)
+        for (size_t i = 0; i < (size_t)n_chains * 3; i++)
+            NEED(ctx, mt_state[i * MT_WORDS + MT_N] <= (uint32_t)MT_N, "Error: RNG state %zu has mti %u > 624", i,
+                 mt_state[i * MT_WORDS + MT_N]);
     if (int r = alloc_chain_buffers(ctx, n_chains, first_chain)) return r;
     const size_t S3 = (size_t)ctx->sys.n_sites * 3;
     if (n_structs == n_chains) {
@@ -720,8 +556,8 @@ extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t fi
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
-    DevBuf<long long> d_seeds;
-    DevBuf<int> d_idx, d_pos;
+    DevBuf<long long> &d_seeds = ctx->d_seeds;
+    DevBuf<int> &d_idx = ctx->d_sched_idx, &d_pos = ctx->d_mt_pos;
     std::vector<uint32_t> words;
     std::vector<int> pos;
     if (mt_state) {
@@ -729,9 +565,7 @@ extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t fi
         pos.resize((size_t)n_chains * 3);
         for (size_t i = 0; i < (size_t)n_chains * 3; i++) {
             memcpy(words.data() + i * 2 * MT_N, mt_state + i * MT_WORDS, MT_N * 4);   // buffer 0 of the ping-pong pair
-            const uint32_t mti = mt_state[i * MT_WORDS + MT_N];
-            NEED(ctx, mti <= (uint32_t)MT_N, "Error: RNG state %zu has mti %u > 624", i, mti);
-            pos[i] = (int)mti;
+            pos[i] = (int)mt_state[i * MT_WORDS + MT_N];
         }
         CK(ctx, cudaMemcpyAsync(ctx->d_mt.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(ctx, d_pos.alloc(pos.size()));
@@ -744,9 +578,42 @@ extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t fi
         CK(ctx, d_idx.alloc((size_t)n_chains));
         CK(ctx, cudaMemcpyAsync(d_idx.p, sched_idx, (size_t)n_chains * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (int r = launch_init(ctx, mt_state ? nullptr : d_seeds.p, d_idx.p, mt_state ? d_pos.p : nullptr, space_len, 0, 0)) return r;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (int r = launch_init(ctx, mt_state ? nullptr : d_seeds.p, sched_idx ? d_idx.p : nullptr, mt_state ? d_pos.p : nullptr, space_len, 0, 0))
+        return r;
+    return commit_chains(ctx);     // (also keeps the host staging vectors alive until the copies have landed)
+}
+
+extern "C" int tr_set_kernel(tr_ctx *ctx, int32_t kernel, int32_t chains_per_block, int32_t blocks_per_sm)
+{
+    if (!ctx) return TR_EINVAL;
+    NEED(ctx, kernel == TR_KERNEL_AUTO || kernel == TR_KERNEL_TEAM || kernel == TR_KERNEL_CREW,
+         "Error: kernel must be TR_KERNEL_AUTO, TR_KERNEL_TEAM or TR_KERNEL_CREW");
+    NEED(ctx, chains_per_block >= 0 && chains_per_block <= 32 && blocks_per_sm >= 0 && blocks_per_sm <= 8,
+         "Error: chains_per_block must be 0..32 and blocks_per_sm 0..8");
+    ctx->kernel_choice = kernel;
+    ctx->crew_chains = chains_per_block;
+    ctx->crew_bps = blocks_per_sm;
     return TR_OK;
+}
+
+extern "C" const char *tr_kernel_name(const tr_ctx *ctx) { return ctx ? ctx->kernel_name.c_str() : ""; }
+
+extern "C" int tr_abi_sizes(int32_t *out, int32_t cap)
+{
+    // sizeof and the offsets a binding cannot derive from natural alignment alone: checked at load time by
+    // transrot_b200/engine.py and java/TransRotB200.java instead of by comment
+    const int32_t v[] = {
+        (int32_t)sizeof(tr_system), (int32_t)offsetof(tr_system, mol_site_off), (int32_t)offsetof(tr_system, pair_abcd),
+        (int32_t)sizeof(tr_schedule), (int32_t)offsetof(tr_schedule, moves_per_point), (int32_t)offsetof(tr_schedule, write_conf_heat_capacities),
+        (int32_t)sizeof(tr_point_rec), (int32_t)offsetof(tr_point_rec, temp), (int32_t)offsetof(tr_point_rec, movie_energy),
+        (int32_t)sizeof(tr_trace_rec), (int32_t)offsetof(tr_trace_rec, e_start), (int32_t)offsetof(tr_trace_rec, running),
+        (int32_t)sizeof(tr_chain_summary), (int32_t)offsetof(tr_chain_summary, moves), (int32_t)offsetof(tr_chain_summary, min_tooth),
+        (int32_t)sizeof(tr_minimum), (int32_t)offsetof(tr_minimum, chain), (int32_t)offsetof(tr_minimum, tooth),
+    };
+    const int32_t n = (int32_t)(sizeof v / sizeof v[0]);
+    if (!out || cap < n) return n;
+    for (int32_t i = 0; i < n; i++) out[i] = v[i];
+    return n;
 }
 
 // ===================================================================================== hot path
@@ -772,7 +639,7 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     P.trace = ctx->d_trace.p;
     P.n_chains = ctx->n_chains;
     P.max_moves = max_moves;
-    P.trace_moves = ctx->trace_moves;
+    P.trace_moves = ctx->live_trace_moves;
     P.max_points = ctx->max_points;
     P.max_snaps = ctx->max_snaps;
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -816,13 +683,18 @@ extern "C" int tr_get_summary(tr_ctx *ctx, tr_chain_summary *out)
     if (int r = bind(ctx)) return r;
     if (int r = need_chains(ctx)) return r;
     NEED(ctx, out != nullptr, "Error: tr_get_summary: out is NULL");
-    DevBuf<tr_chain_summary> d;
+    DevBuf<tr_chain_summary> &d = ctx->d_summary;
     CK(ctx, d.alloc((size_t)ctx->n_chains));
     summary_kernel<<<(unsigned)((ctx->n_chains + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ctrl.p, ctx->n_chains, d.p);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpyAsync(out, d.p, (size_t)ctx->n_chains * sizeof(tr_chain_summary), cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    // a chain the kernel had to abandon is an error of the run, not a result (the records are still returned)
+    for (long long i = 0; i < ctx->n_chains; i++)
+        if (out[i].done == 2)
+            return fail(ctx, TR_ERNG, "Error: chain %lld was abandoned after %lld moves: its random stream ring could not be refilled",
+                        (long long)(ctx->first_chain + i), (long long)out[i].moves);
     return TR_OK;
 }
 
@@ -906,7 +778,7 @@ extern "C" int tr_get_trace(tr_ctx *ctx, tr_trace_rec *out)
     if (int r = bind(ctx)) return r;
     if (int r = need_chains(ctx)) return r;
     NEED(ctx, ctx->d_trace.p && out, "Error: tracing was not enabled with tr_set_options");
-    CK(ctx, cudaMemcpyAsync(out, ctx->d_trace.p, (size_t)ctx->n_chains * (size_t)ctx->trace_moves * sizeof(tr_trace_rec),
+    CK(ctx, cudaMemcpyAsync(out, ctx->d_trace.p, (size_t)ctx->n_chains * (size_t)ctx->live_trace_moves * sizeof(tr_trace_rec),
                             cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return TR_OK;
@@ -918,7 +790,7 @@ extern "C" int tr_get_rng_state(tr_ctx *ctx, uint32_t *out)
     if (int r = bind(ctx)) return r;
     if (int r = need_chains(ctx)) return r;
     NEED(ctx, out != nullptr, "Error: tr_get_rng_state: out is NULL");
-    DevBuf<uint32_t> d_out;
+    DevBuf<uint32_t> &d_out = ctx->d_rng_out;
     CK(ctx, d_out.alloc((size_t)ctx->n_chains * 3 * MT_WORDS));
     const long long threads = ctx->n_chains * 32;
     rng_export_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ctrl.p, ctx->d_mt.p, ctx->n_chains, d_out.p);
@@ -935,9 +807,8 @@ extern "C" int tr_pack_minima(tr_ctx *ctx, tr_minimum *host_out, void *device_ou
     if (int r = bind(ctx)) return r;
     if (int r = need_chains(ctx)) return r;
     NEED(ctx, host_out || device_out, "Error: tr_pack_minima: no output buffer");
-    DevBuf<tr_minimum> tmp;
     tr_minimum *dst = (tr_minimum *)device_out;
-    if (!dst) { CK(ctx, tmp.alloc((size_t)ctx->n_chains)); dst = tmp.p; }
+    if (!dst) { CK(ctx, ctx->d_minima.alloc((size_t)ctx->n_chains)); dst = ctx->d_minima.p; }
     pack_minima_kernel<<<(unsigned)((ctx->n_chains + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ctrl.p, ctx->n_chains, ctx->first_chain, dst);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
@@ -972,6 +843,30 @@ extern "C" int tr_get_min_structure(tr_ctx *ctx, int64_t chain, double *sites, d
                                 ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return TR_OK;
+}
+
+extern "C" int tr_pack_min_structures(tr_ctx *ctx, int64_t first, int64_t count, double *host_out, void *device_out)
+{
+    if (!ctx) return TR_EINVAL;
+    if (int r = bind(ctx)) return r;
+    if (int r = need_chains(ctx)) return r;
+    NEED(ctx, host_out || device_out, "Error: tr_pack_min_structures: no output buffer");
+    NEED(ctx, first >= 0 && count > 0 && first + count <= ctx->n_chains, "Error: tr_pack_min_structures: chains %lld..%lld out of range",
+         (long long)first, (long long)(first + count - 1));
+    NEED(ctx, ctx->d_snap_sites.p != nullptr, "Error: snapshot structures were disabled with tr_set_options");
+    const size_t row = (size_t)ctx->sys.n_sites * 3;
+    double *dst = (double *)device_out;
+    if (!dst) { CK(ctx, ctx->d_min_sites.alloc((size_t)count * row)); dst = ctx->d_min_sites.p; }
+    const long long total = count * (long long)row;
+    const size_t K = (size_t)ctx->max_snaps;
+    pack_min_structures_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 65535LL * 16), 256, 0, ctx->stream>>>(
+        ctx->d_snap_energy.p + (size_t)first * K, ctx->d_snap_tooth.p + (size_t)first * K, ctx->d_snap_sites.p + (size_t)first * K * row, count,
+        ctx->max_snaps, (int)row, dst);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    if (host_out) CK(ctx, cudaMemcpyAsync(host_out, dst, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     return TR_OK;
 }
 

@@ -92,7 +92,30 @@ _SIGNATURES = {
     "tr_delta_energy": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "tr_rng_words": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p],
     "tr_measure_fp64_peak": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "tr_set_kernel": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32],
+    "tr_abi_sizes": [C.c_void_p, C.c_int32],
+    "tr_kernel_name": [C.c_void_p],
+    "tr_pack_min_structures": [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p],
+    # multi-GPU, one host thread (csrc/multi.cu)
+    "tr_create_multi": [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)],
+    "tr_destroy_multi": [C.c_void_p],
+    "tr_multi_last_error": [C.c_void_p],
+    "tr_multi_size": [C.c_void_p],
+    "tr_multi_ctx": [C.c_void_p, C.c_int32],
+    "tr_multi_chain_range": [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    "tr_multi_set_system": [C.c_void_p, C.POINTER(TrSystem)],
+    "tr_multi_set_schedules": [C.c_void_p, C.c_void_p, C.c_int32],
+    "tr_multi_set_options": [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32],
+    "tr_multi_init_chains_seeded": [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_int32],
+    "tr_multi_run": [C.c_void_p, C.c_int64],
+    "tr_multi_synchronize": [C.c_void_p],
+    "tr_multi_last_run_ms": [C.c_void_p, C.POINTER(C.c_float)],
+    "tr_gather_minima": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "tr_gather_min_structures": [C.c_void_p, C.c_void_p],
 }
+_RESTYPES = {"tr_destroy": None, "tr_destroy_multi": None, "tr_multi_chain_range": None, "tr_last_error": C.c_char_p,
+             "tr_multi_last_error": C.c_char_p, "tr_kernel_name": C.c_char_p, "tr_multi_ctx": C.c_void_p, "tr_multi_size": C.c_int32}
+TR_KERNEL_AUTO, TR_KERNEL_TEAM, TR_KERNEL_CREW = 0, 1, 2
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
@@ -112,9 +135,28 @@ def load_library() -> C.CDLL:
     for name, args in _SIGNATURES.items():
         fn = getattr(L, name)
         fn.argtypes = args
-        fn.restype = None if name == "tr_destroy" else (C.c_char_p if name == "tr_last_error" else C.c_int)
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _check_abi(L)
     _lib = L
     return L
+
+
+def _check_abi(L: C.CDLL):
+    """The struct layouts of this module against the library's own sizeof / offsetof (tr_abi_sizes)."""
+    n = L.tr_abi_sizes(None, 0)
+    got = (C.c_int32 * n)()
+    L.tr_abi_sizes(got, n)
+    off = lambda dt, f: dt.fields[f][1]
+    want = [
+        C.sizeof(TrSystem), TrSystem.mol_site_off.offset, TrSystem.pair_abcd.offset,
+        SCHEDULE_DTYPE.itemsize, off(SCHEDULE_DTYPE, "moves_per_point"), off(SCHEDULE_DTYPE, "write_conf_heat_capacities"),
+        POINT_DTYPE.itemsize, off(POINT_DTYPE, "temp"), off(POINT_DTYPE, "movie_energy"),
+        TRACE_DTYPE.itemsize, off(TRACE_DTYPE, "e_start"), off(TRACE_DTYPE, "running"),
+        SUMMARY_DTYPE.itemsize, off(SUMMARY_DTYPE, "moves"), off(SUMMARY_DTYPE, "min_tooth"),
+        MINIMUM_DTYPE.itemsize, off(MINIMUM_DTYPE, "chain"), off(MINIMUM_DTYPE, "tooth"),
+    ]
+    if list(got) != want:
+        raise TransRotError(f"Error: struct layouts of {LIB_PATH} differ from this binding: library {list(got)}, binding {want}")
 
 
 def schedule_from_config(cfg: Config) -> np.ndarray:
@@ -154,12 +196,26 @@ class Engine:
         self.h = h
         self.system: Optional[System] = None
         self.n_chains = 0
-        self.trace_moves = 0
-        self._keep = []
+        self.trace_moves = 0          # pending option
+        self.live_trace_moves = 0     # what the live chain batch was allocated with
+        self._owned = True
+
+    @classmethod
+    def _borrow(cls, handle, system=None):
+        """An Engine view of a context owned by a MultiEngine."""
+        e = cls.__new__(cls)
+        e.L = load_library()
+        e.h = C.c_void_p(handle)
+        e.system = system
+        e.n_chains = 0
+        e.trace_moves = e.live_trace_moves = 0
+        e._owned = False
+        return e
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.tr_destroy(self.h)
+            if self._owned:
+                self.L.tr_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -216,12 +272,23 @@ class Engine:
         self._ck(self.L.tr_set_options(self.h, int(trace_moves), int(record_points), int(record_snapshots), int(threads_per_chain)))
         self.trace_moves = int(trace_moves)
 
+    def set_kernel(self, kernel: int = TR_KERNEL_AUTO, chains_per_block: int = 0, blocks_per_sm: int = 0):
+        """Kernel family / launch geometry for the next init_chains_* (experiments and tests; 0 = automatic)."""
+        self._ck(self.L.tr_set_kernel(self.h, int(kernel), int(chains_per_block), int(blocks_per_sm)))
+
+    def kernel_name(self) -> str:
+        return (self.L.tr_kernel_name(self.h) or b"").decode()
+
     def init_chains_seeded(self, seeds: Sequence[int], space_len: float, max_prop_failures: int,
                            sched_idx: Optional[Sequence[int]] = None, first_chain: int = 0):
         s = np.ascontiguousarray(seeds, dtype=np.int64)
         idx = None if sched_idx is None else np.ascontiguousarray(sched_idx, dtype=np.int32)
+        if idx is not None and len(idx) != len(s):
+            raise TransRotError(f"Error: {len(s)} seeds but {len(idx)} schedule indices")
+        self.n_chains = 0
         self._ck(self.L.tr_init_chains_seeded(self.h, len(s), int(first_chain), s.ctypes.data, _ptr(idx), float(space_len), int(max_prop_failures)))
         self.n_chains = len(s)
+        self.live_trace_moves = self.trace_moves
 
     def init_chains_explicit(self, n_chains: int, sites: np.ndarray, space_len: float, seeds: Optional[Sequence[int]] = None,
                              mt_state: Optional[np.ndarray] = None, sched_idx: Optional[Sequence[int]] = None, first_chain: int = 0):
@@ -230,8 +297,16 @@ class Engine:
         sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.int64)
         st = None if mt_state is None else np.ascontiguousarray(mt_state, dtype=np.uint32).reshape(n_chains, 3, 625)
         idx = None if sched_idx is None else np.ascontiguousarray(sched_idx, dtype=np.int32)
+        n_chains = int(n_chains)
+        if x.shape[0] not in (1, n_chains):
+            raise TransRotError(f"Error: {x.shape[0]} structures for {n_chains} chains (give 1 or one per chain)")
+        for name, a in (("seeds", sd), ("schedule indices", idx)):
+            if a is not None and len(a) != n_chains:
+                raise TransRotError(f"Error: {len(a)} {name} for {n_chains} chains")
+        self.n_chains = 0
         self._ck(self.L.tr_init_chains_explicit(self.h, int(n_chains), int(first_chain), x.ctypes.data, x.shape[0], _ptr(sd), _ptr(st), _ptr(idx), float(space_len)))
         self.n_chains = int(n_chains)
+        self.live_trace_moves = self.trace_moves
 
     # ---- hot path
     def run(self, max_moves: int = 0):
@@ -291,7 +366,7 @@ class Engine:
         return out
 
     def trace(self) -> np.ndarray:
-        out = np.zeros((self.n_chains, self.trace_moves), dtype=TRACE_DTYPE)
+        out = np.zeros((self.n_chains, self.live_trace_moves), dtype=TRACE_DTYPE)
         self._ck(self.L.tr_get_trace(self.h, out.ctypes.data))
         return out
 
@@ -313,6 +388,17 @@ class Engine:
         e, t = C.c_double(), C.c_int32()
         self._ck(self.L.tr_get_min_structure(self.h, int(chain), x.ctypes.data, C.byref(e), C.byref(t)))
         return x, float(e.value), int(t.value)
+
+    def min_structures(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """[count, S, 3]: the write(min_tooth) structure of chains first .. first+count-1, packed on the device."""
+        count = self.n_chains - first if count is None else count
+        out = np.zeros((count, self.system.n_sites, 3), dtype=np.float64)
+        self._ck(self.L.tr_pack_min_structures(self.h, int(first), int(count), out.ctypes.data, None))
+        return out
+
+    def pack_min_structures_device(self, device_ptr: int, first: int = 0, count: Optional[int] = None):
+        count = self.n_chains - first if count is None else count
+        self._ck(self.L.tr_pack_min_structures(self.h, int(first), int(count), None, C.c_void_p(device_ptr)))
 
     # ---- probes
     def total_energy(self, sites: np.ndarray) -> np.ndarray:
@@ -347,3 +433,116 @@ class Engine:
         t, mhz = C.c_double(), C.c_double()
         self._ck(self.L.tr_measure_fp64_peak(self.h, C.byref(t), C.byref(mhz)))
         return float(t.value), float(mhz.value)
+
+
+class MultiEngine:
+    """One tr_multi: every GPU of a box driven from one host thread (csrc/multi.cu), the way a single-JVM host
+    would.  Chains are sharded in contiguous global ranges; the final gather runs over NCCL."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.L = load_library()
+        d = (C.c_int32 * len(devices))(*[int(x) for x in devices])
+        h = C.c_void_p()
+        rc = self.L.tr_create_multi(d, len(devices), C.byref(h))
+        if rc != 0:
+            raise TransRotError((self.L.tr_multi_last_error(None) or b"").decode() or f"tr_create_multi failed ({rc})")
+        self.h = h
+        self.devices = list(devices)
+        self.system: Optional[System] = None
+        self.n_chains = 0
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tr_destroy_multi(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise TransRotError((self.L.tr_multi_last_error(self.h) or b"").decode() or f"error {rc}")
+
+    def chain_range(self, i: int, n_total: Optional[int] = None):
+        lo, hi = C.c_int64(), C.c_int64()
+        self.L.tr_multi_chain_range(int(i), len(self.devices), int(self.n_chains if n_total is None else n_total), C.byref(lo), C.byref(hi))
+        return int(lo.value), int(hi.value)
+
+    def ctx(self, i: int) -> Engine:
+        """Per-device view for the tr_get_* calls (local chain j of device i is global chain lo_i + j)."""
+        e = Engine._borrow(self.L.tr_multi_ctx(self.h, int(i)), self.system)
+        lo, hi = self.chain_range(i)
+        e.n_chains = hi - lo
+        return e
+
+    def set_system(self, system: System):
+        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        arrs = dict(
+            mol_site_off=c(system.mol_site_off, np.int32), mol_radius=c(system.mol_radius, np.float64),
+            site_type=c(system.site_type, np.int32), site_q=c(system.site_q, np.float64),
+            site_def=c(system.site_def, np.float64), site_mass=c(system.site_mass, np.float64),
+            site_ghost=c(system.site_ghost, np.int32), moveable_idx=c(system.moveable_idx, np.int32),
+            pair_abcd=c(system.pair_table, np.float64),
+        )
+        ts = TrSystem(n_mol=system.n_mol, n_sites=system.n_sites, n_types=system.n_types, n_moveable=len(system.moveable_idx),
+                      **{k: v.ctypes.data for k, v in arrs.items()})
+        self._ck(self.L.tr_multi_set_system(self.h, C.byref(ts)))
+        self.system = system
+        self.n_chains = 0
+
+    def set_schedules(self, schedules):
+        if isinstance(schedules, Config):
+            arr = schedule_from_config(schedules)
+        elif isinstance(schedules, np.ndarray):
+            arr = np.ascontiguousarray(schedules, dtype=SCHEDULE_DTYPE)
+        else:
+            arr = np.concatenate([schedule_from_config(c) for c in schedules])
+        self._ck(self.L.tr_multi_set_schedules(self.h, arr.ctypes.data, len(arr)))
+        self.n_chains = 0
+
+    def set_options(self, trace_moves: int = 0, record_points: bool = True, record_snapshots: bool = True, threads_per_chain: int = 0):
+        self._ck(self.L.tr_multi_set_options(self.h, int(trace_moves), int(record_points), int(record_snapshots), int(threads_per_chain)))
+
+    def init_chains_seeded(self, seeds: Sequence[int], space_len: float, max_prop_failures: int,
+                           sched_idx: Optional[Sequence[int]] = None, first_chain: int = 0):
+        s = np.ascontiguousarray(seeds, dtype=np.int64)
+        idx = None if sched_idx is None else np.ascontiguousarray(sched_idx, dtype=np.int32)
+        if idx is not None and len(idx) != len(s):
+            raise TransRotError(f"Error: {len(s)} seeds but {len(idx)} schedule indices")
+        self.n_chains = 0
+        self._ck(self.L.tr_multi_init_chains_seeded(self.h, len(s), int(first_chain), s.ctypes.data, _ptr(idx), float(space_len), int(max_prop_failures)))
+        self.n_chains = len(s)
+
+    def run(self, max_moves: int = 0):
+        self._ck(self.L.tr_multi_run(self.h, int(max_moves)))
+
+    def synchronize(self):
+        self._ck(self.L.tr_multi_synchronize(self.h))
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self.L.tr_multi_last_run_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def gather_minima(self, with_structure: bool = True):
+        """(all records ordered by global chain id, winner record, winner structure [S, 3] or None)."""
+        allm = np.zeros(self.n_chains, dtype=MINIMUM_DTYPE)
+        best = np.zeros(1, dtype=MINIMUM_DTYPE)
+        x = np.zeros((self.system.n_sites, 3), dtype=np.float64) if with_structure else None
+        self._ck(self.L.tr_gather_minima(self.h, allm.ctypes.data, best.ctypes.data, _ptr(x)))
+        return allm, best[0], x
+
+    def gather_min_structures(self) -> np.ndarray:
+        out = np.zeros((self.n_chains, self.system.n_sites, 3), dtype=np.float64)
+        self._ck(self.L.tr_gather_min_structures(self.h, out.ctypes.data))
+        return out

@@ -198,6 +198,36 @@ class Config:
     def total_moves(self) -> int:
         return self.num_points() * self.movePerPt
 
+    def to_text(self) -> str:
+        """A config.txt the reference's own parser accepts (Config.java:36-48,102-169): what tools/jvm_pin.sh feeds
+        the JVM.  Doubles are written in plain decimal notation (the reference's DOUBLE regex has no exponent)."""
+        def d(x: float) -> str:
+            t = repr(float(x))
+            if "e" in t or "E" in t:
+                t = f"{float(x):.17f}".rstrip("0")
+                t += "0" if t.endswith(".") else ""
+            return t
+        b = lambda v: "true" if v else "false"
+        rows = [
+            ("Max Temperature (K)", d(self.maxTemp)), ("Moves per Point", str(self.movePerPt)),
+            ("Points per Tooth", str(self.ptsPerTooth)), ("Points Added per Tooth", str(self.ptsAddedPerTooth)),
+            ("Number of Teeth", str(self.numTeeth)), ("Temperature Decrease per Tooth", d(self.tempDecreasePerTooth)),
+            ("Max Translation Distance (Angstroms)", d(self.maxTrans)),
+            ("Magwalk Translation Multiplication Factor", d(self.magwalkFactorTrans)),
+            ("Magwalk Translation Probability", d(self.magwalkProbTrans)), ("Max Rotation (Radians)", d(self.maxRot)),
+            ("Magwalk Rotation Probability", d(self.magwalkProbRot)), ("Length of Cubic Space", d(self.spaceLen)),
+            ("Max Failures During Propagation", str(self.maxPropFailures)), ("Use Input.xyz (true/false)", b(self.useInput)),
+            ("Choose All Interaction Parameters (true/false)", b(self.chooseParams)), ("0K Finale (true/false)", b(self.finale)),
+            ("Static Temperature (true/false)", b(self.staticTemp)),
+            ("Write Energies When Static Temperature (true/false)", b(self.writeEnergiesEnabled)),
+            ("Write Configurational Heat Capacities (true/false)", b(self.writeConfHeatCapacitiesEnabled)),
+            ("Number of Equilibration Configurations", str(self.eqConfigs)),
+            ("Write Acceptance Ratios (true/false)", b(self.writeAcceptanceRatios)),
+        ]
+        out = ["// Sawtooth Annealing Configuration Options"] + [f"{k + ':':<54}{v}" for k, v in rows]
+        out += ["", "// List of Molecules to be Used"] + [f"{n}  {c}" for n, c in self.particles]
+        return "\n".join(out) + "\n"
+
     @staticmethod
     def parseConfig(filename: str) -> "Config":
         """Config.parseConfig (Config.java:102-169).  Particle lines are returned in file order; the caller
