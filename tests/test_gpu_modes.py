@@ -27,7 +27,9 @@ def _check_records(engine, dbase, cfg, seeds, pair_table=None, trace_moves=0):
         e0 = sp.write_snapshot(0)
         res = sp.sawtooth_anneal(e0, points_cap=cfg.num_points() + 4, snap_cap=cfg.numTeeth + 2, trace_cap=trace_moves)
         assert summ["done"][i] == 1 and summ["moves"][i] == res.moves
-        assert summ["evaluated"][i] == res.evaluated and summ["pair_evals"][i] == res.pair_evals
+        assert summ["evaluated"][i] == res.evaluated
+        # executed pair evaluations: eStart + eEnd like the reference, or eEnd only (crew2 takes eStart from its pair cache)
+        assert summ["pair_evals"][i] in (res.pair_evals, res.pair_evals // 2)
         assert summ["points"][i] == len(res.points)
         p = pts[i, : len(res.points)]
         for key in ("tooth", "point", "accepted", "total", "movie_written", "finale"):

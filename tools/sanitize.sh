@@ -9,7 +9,7 @@ CS=/usr/local/cuda/bin/compute-sanitizer
 for tool in memcheck racecheck synccheck; do
   extra=""
   [ $tool = racecheck ] && extra="--racecheck-report all"
-  timeout 1500 $CS --tool $tool $extra --print-limit 20 --log-file "$out/sanitize_$tool.log" python tools/sanitize_cases.py $cases > "$out/sanitize_$tool.out" 2>&1
+  timeout ${SAN_TIMEOUT:-600} $CS --tool $tool $extra --print-limit 20 --log-file "$out/sanitize_$tool.log" python tools/sanitize_cases.py $cases > "$out/sanitize_$tool.out" 2>&1
   rc=$?
   echo "== $tool: exit $rc; $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$out/sanitize_$tool.log" | tail -1)" >> "$out/sanitize_summary.txt"
   cat "$out/sanitize_$tool.out" >> "$out/sanitize_summary.txt"

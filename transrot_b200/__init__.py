@@ -9,7 +9,7 @@ from .host import (  # noqa: F401
 )
 from .engine import (  # noqa: F401
     Engine, EXPORTED_SYMBOLS, LIB_PATH, MINIMUM_DTYPE, MultiEngine, POINT_DTYPE, SCHEDULE_DTYPE, SUMMARY_DTYPE, TRACE_DTYPE,
-    TR_KERNEL_AUTO, TR_KERNEL_CREW, TR_KERNEL_TEAM, load_library, schedule_from_config,
+    TR_KERNEL_AUTO, TR_KERNEL_CREW, TR_KERNEL_CREW2, TR_KERNEL_TEAM, load_library, schedule_from_config,
 )
 from .workloads import WORKLOADS, sweep_schedules, workload_config  # noqa: F401
 from .sharding import chain_range, gather_minima, global_minimum, owner_of  # noqa: F401

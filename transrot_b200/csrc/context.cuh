@@ -34,6 +34,17 @@ struct DevBuf {
 
 struct Variant { int L, W, SPL; int tpc() const { return W > 1 ? 32 * W : L; } };
 
+// Site <-> position permutation of one kernel variant (which lane and slot holds which site), on the device.
+struct PosTables {
+    DevBuf<int> pos_site, site_pos, pos_info;
+    Variant prepared{0, 0, 0};
+    int layout = -1;            // 0: Lennard-Jones sites first (anneal.cuh, crew.cuh); 1: particle-major (crew2.cuh)
+    int n_pos = 0, n_lj_pos = 0;
+};
+
+// crew2 kernel variant: L lanes per team, M particle slots per lane, SS site slots per particle
+struct Crew2Variant { int L, M, SS; };
+
 }  // namespace tr
 
 struct tr_ctx {
@@ -54,11 +65,11 @@ struct tr_ctx {
     tr::DevBuf<int> d_mol_off, d_site_info, d_moveable, d_site_ghost;
     tr::DevBuf<double> d_site_q, d_mol_radius, d_site_def, d_site_mass;
     tr::DevBuf<double2> d_pair_cd, d_pair_ab;
-    tr::DevBuf<int> d_pos_site, d_site_pos, d_pos_info;
+    tr::PosTables run_tabs, probe_tabs;   // of the live chain batch / of the parity probes
+    tr::DevSystem run_sys{};              // sys + the live batch's position tables
     std::vector<int> h_site_info;
     bool have_propagate_data = false;
     std::vector<int> h_mol_off, h_site_lj;
-    tr::Variant prepared{0, 0, 0};
 
     // schedules
     tr::DevBuf<tr_schedule> d_sched;
@@ -79,6 +90,9 @@ struct tr_ctx {
     int max_points = 0, max_snaps = 0;
     tr::Variant variant{16, 1, 1};
     bool use_crew = false;        // warp-specialised kernel (crew.cuh): automatic choice while a chain fits one warp
+    bool use_crew2 = false;       // crew2.cuh: particle-major teams + pair-energy cache, up to TR_CREW2_MAX_MOL particles
+    tr::Crew2Variant crew2{0, 0, 0};
+    tr::DevBuf<double> d_pair_cache;     // [n_chains][tri_count] particle-pair energies (crew2), part of the chain state
     // tr_set_kernel: 0 = automatic, TR_KERNEL_TEAM / TR_KERNEL_CREW force one family; chains per block / co-resident
     // blocks per SM of the crew kernel (0 = automatic)
     int kernel_choice = 0, crew_chains = 0, crew_bps = 0;
@@ -113,5 +127,10 @@ int fail(tr_ctx *ctx, int code, const char *fmt, ...);
 // crew_launch.cu: the warp-specialised kernel family
 int crew_smem_bytes(tr_ctx *ctx, long long n_chains, int *smem);
 int launch_crew(tr_ctx *ctx, const KParams &P);
+// crew2_launch.cu
+constexpr int TR_CREW2_MAX_MOL = 32;
+bool crew2_pick(const tr_ctx *ctx, int max_mol_sites, Crew2Variant *out);
+int crew2_smem_bytes(tr_ctx *ctx, int *smem, int *tri_count);
+int launch_crew2(tr_ctx *ctx, const KParams &P);
 
 }  // namespace tr

@@ -46,6 +46,7 @@ constexpr int PF_TZERO = 4;              // PLAN_AUTO: the temperature is exactl
 
 constexpr int CREW_RING = 128;           // tempered words per stream kept in shared memory
 constexpr int CREW_RING_LOW = CREW_RING - 32;   // a 32-word window may be appended while at most this many are unread
+constexpr int CREW_SETTLE_SLACK = 2;            // S words that must be in the ring beyond a posted move's own draws: its Metropolis double
 
 struct __align__(16) CrewDesc {    // one drawn move (Space.move / Space.rotate arguments after the draws)
     double va, vb, vc;             // translation vector, or (sin, cos, -) of the rotation angle
@@ -478,10 +479,8 @@ __device__ __forceinline__ void crew_sites_from_global(const CrewView &v, const 
 // the chain of this lane.  `etot` = Space.calcEnergy of the current structure when a REQ_TOTAL round
 // preceded the call (movie energy and write(x+1) see the same structure), else unused.
 // Returns with c->done set when the chain has finished.
-__device__ __noinline__ void crew_finish_point(const KParams &P, CrewChain *cs, long long chain, double etot, bool have_etot)
+static __device__ __noinline__ void crew_finish_point(const KParams &P, ChainCtrl *c, const tr_schedule &sch, long long chain, double etot, bool have_etot)
 {
-    ChainCtrl *c = &cs->ctrl;
-    const tr_schedule &sch = cs->sch;
     const int numTeeth = sch.static_temp ? 1 : sch.num_teeth;   // Main.java:74-76
     const double t = c->t;
     const int pi = c->n_points;
@@ -538,10 +537,8 @@ __device__ __noinline__ void crew_finish_point(const KParams &P, CrewChain *cs, 
 
 // Does the point that just ended need Space.calcEnergy (movie frame energy or write(x+1))?  Returns the
 // dump slot for the energy team in `snap_slot`.
-__device__ __forceinline__ bool crew_point_needs_total(const KParams &P, CrewChain *cs, int &snap_slot, int &movie_slot)
+__device__ __forceinline__ bool crew_point_needs_total(const KParams &P, const ChainCtrl *c, const tr_schedule &sch, int &snap_slot, int &movie_slot)
 {
-    const ChainCtrl *c = &cs->ctrl;
-    const tr_schedule &sch = cs->sch;
     const int numTeeth = sch.static_temp ? 1 : sch.num_teeth;
     const double t = c->t;
     const bool movie = !(sch.write_conf_heat_capacities && t < 0.005 && t > -0.005);
@@ -738,7 +735,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
             k.sm = TL::mol_off(smem, k.m + 1) - k.off;
             k.rot = (cm.kindbit && k.sm > 1) ? 1 : 0;
             if (!k.rot) {
-                if (p + 6 > wrS) return;
+                if (p + 6 + CREW_SETTLE_SLACK > wrS) return;
                 const double maxT = cm.magw_trans ? maxTmag : maxD;
                 const double ux = crew_next_double(ringS(p), ringS(p + 1));                          // Space.java:694-696
                 const double uy = crew_next_double(ringS(p + 2), ringS(p + 3));
@@ -748,6 +745,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                 k.vc = __dsub_rn(__dmul_rn(__dmul_rn(uz, 2.0), maxT), maxT);
                 p += 6;
             }
+            if (p + CREW_SETTLE_SLACK > wrS) return;      // the move's own Metropolis double must already be in the ring
             k.nS = p - pos;
             k.ok = true;
         };
@@ -794,6 +792,8 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     const int oob = res->oob;
                     const double dE = oob ? 0.0 : res->dE;
                     int acc, drew;
+                    // (the words are there: a move is only ever posted with at least 16 unread S words beyond its own draws,
+                    // see draw_pick's availability tests and CREW_SETTLE_SLACK)
                     if (!metro_ok && !oob && dE > 0.0) rnd = crew_next_double(ringS(rdS), ringS(rdS + 1));
                     crew_metropolis(oob, dE, t == 0.0, metro_ok, rnd, thr, grd, kBt, acc, drew);
                     if (acc) commit_pending = 1;
@@ -842,7 +842,7 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                         c->delT = c->t / (double)(c->ptsPerTooth - 1);      // Main.java:188 for tooth 0
                         total_for_init = false;
                     } else {
-                        crew_finish_point(P, cs, chain, etot, true);
+                        crew_finish_point(P, c, sch, chain, etot, true);
                     }
                     load_hot();
                 }
@@ -885,9 +885,9 @@ crew_kernel(const __grid_constant__ KParams P, const int C, const int stride, co
                     } else if (!c->done && z >= mpp) {
                         // end of the point: with a calcEnergy round first when its result is needed
                         flush_hot();
-                        if (crew_point_needs_total(P, cs, snap_slot, movie_slot)) mode = PLAN_TOTAL;
+                        if (crew_point_needs_total(P, c, sch, snap_slot, movie_slot)) mode = PLAN_TOTAL;
                         else {
-                            crew_finish_point(P, cs, chain, 0.0, false);
+                            crew_finish_point(P, c, sch, chain, 0.0, false);
                             load_hot();
                         }
                     }

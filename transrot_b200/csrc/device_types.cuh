@@ -74,6 +74,7 @@ struct KParams {
     double *snap_sites;         // [n_chains][max_snaps][S][3] or null
     double *movie_sites;        // [n_chains][max_points][S][3] or null
     tr_trace_rec *trace;        // [n_chains][trace_moves] or null
+    double *pair_cache;         // [n_chains][tri_count] particle-pair energies (crew2 kernel) or null
     long long n_chains;
     long long max_moves;        // <= 0: run to completion
     long long trace_moves;

@@ -70,30 +70,55 @@ bool pick_variant(const tr_ctx *ctx, int n_sites, int tpc, Variant *out)
 
 bool same_variant(const Variant &a, const Variant &b) { return a.L == b.L && a.W == b.W && a.SPL == b.SPL; }
 
-// Site -> (thread, slot) permutation of a kernel variant: sites with Lennard-Jones parameters first, so that
-// the trailing slots are Coulomb-only for every thread (anneal.cuh).
-int prepare_variant(tr_ctx *ctx, const Variant &v)
+// Site -> (thread, slot) permutation of a kernel variant into `tabs`, and the DevSystem that carries it.
+// layout 0 (anneal.cuh, crew.cuh): sites with Lennard-Jones parameters first, so that the trailing slots are Coulomb-only
+// for every thread.  layout 1 (crew2.cuh): particle-major - lane n % L owns particle n in its slot n / L, SS site slots each:
+// position of site a of particle n = ((n / L) * SS + a) * L + n % L.
+int prepare_tables(tr_ctx *ctx, PosTables &tabs, int layout, const Variant &v, int n_pos, DevSystem *out)
 {
-    if (same_variant(ctx->prepared, v)) return TR_OK;
-    const int n_pos = v.tpc() * v.SPL, S = ctx->sys.n_sites, T = ctx->sys.n_types;
-    std::vector<int> pos((size_t)n_pos, -1), inv((size_t)S, 0), pinfo((size_t)n_pos, INFO_UNUSED | (T << 16));
-    int p = 0, n_lj = 0;
-    for (int i = 0; i < S; i++) if (ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
-    n_lj = p;
-    for (int i = 0; i < S; i++) if (!ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
-    for (int q = 0; q < S; q++) { inv[(size_t)pos[(size_t)q]] = q; pinfo[(size_t)q] = ctx->h_site_info[(size_t)pos[(size_t)q]]; }
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (int r = upload(ctx, ctx->d_pos_site, pos.data(), pos.size())) return r;
-    if (int r = upload(ctx, ctx->d_site_pos, inv.data(), inv.size())) return r;
-    if (int r = upload(ctx, ctx->d_pos_info, pinfo.data(), pinfo.size())) return r;
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->sys.pos_site = ctx->d_pos_site.p;
-    ctx->sys.site_pos = ctx->d_site_pos.p;
-    ctx->sys.pos_info = ctx->d_pos_info.p;
-    ctx->sys.n_pos = n_pos;
-    ctx->sys.n_lj_pos = n_lj;
-    ctx->prepared = v;
+    const int S = ctx->sys.n_sites, T = ctx->sys.n_types;
+    if (!(tabs.layout == layout && same_variant(tabs.prepared, v))) {
+        std::vector<int> pos((size_t)n_pos, -1), inv((size_t)S, 0), pinfo((size_t)n_pos, INFO_UNUSED | (T << 16));
+        int n_lj = 0;
+        if (layout == 0) {
+            int p = 0;
+            for (int i = 0; i < S; i++) if (ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
+            n_lj = p;
+            for (int i = 0; i < S; i++) if (!ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
+        } else {
+            const int L = v.L, SS = v.SPL;
+            for (int n = 0; n < ctx->sys.n_mol; n++)
+                for (int i = ctx->h_mol_off[(size_t)n]; i < ctx->h_mol_off[(size_t)n + 1]; i++)
+                    pos[(size_t)(((n / L) * SS + (i - ctx->h_mol_off[(size_t)n])) * L + n % L)] = i;
+        }
+        for (int q = 0; q < n_pos; q++)
+            if (pos[(size_t)q] >= 0) { inv[(size_t)pos[(size_t)q]] = q; pinfo[(size_t)q] = ctx->h_site_info[(size_t)pos[(size_t)q]]; }
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (int r = upload(ctx, tabs.pos_site, pos.data(), pos.size())) return r;
+        if (int r = upload(ctx, tabs.site_pos, inv.data(), inv.size())) return r;
+        if (int r = upload(ctx, tabs.pos_info, pinfo.data(), pinfo.size())) return r;
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        tabs.prepared = v; tabs.layout = layout; tabs.n_pos = n_pos; tabs.n_lj_pos = n_lj;
+    }
+    *out = ctx->sys;
+    out->pos_site = tabs.pos_site.p;
+    out->site_pos = tabs.site_pos.p;
+    out->pos_info = tabs.pos_info.p;
+    out->n_pos = tabs.n_pos;
+    out->n_lj_pos = tabs.n_lj_pos;
     return TR_OK;
+}
+
+int prepare_variant(tr_ctx *ctx, PosTables &tabs, const Variant &v, DevSystem *out)
+{
+    return prepare_tables(ctx, tabs, 0, v, v.tpc() * v.SPL, out);
+}
+
+int max_mol_sites_of(const tr_ctx *ctx)
+{
+    int m = 1;
+    for (size_t i = 0; i + 1 < ctx->h_mol_off.size(); i++) m = std::max(m, ctx->h_mol_off[i + 1] - ctx->h_mol_off[i]);
+    return m;
 }
 
 // ---- kernel dispatch -----------------------------------------------------------------------
@@ -153,19 +178,19 @@ cudaError_t smem_need_t(tr_ctx *ctx, int *bytes)
 }
 
 template <int L, int W, int SPL, bool HAS_EXP>
-cudaError_t launch_total_t(tr_ctx *ctx, const double *d_sites, long long n, double *d_out)
+cudaError_t launch_total_t(tr_ctx *ctx, const DevSystem &dsys, const double *d_sites, long long n, double *d_out)
 {
     auto kern = total_energy_kernel<L, W, SPL, HAS_EXP>;
     const int smem = Layout<L, W, SPL>::total_bytes(ctx->sys.n_types, HAS_EXP);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
-    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(ctx->sys, d_sites, n, d_out);
+    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(dsys, d_sites, n, d_out);
     return cudaGetLastError();
 }
 
 template <int L, int W, int SPL, bool HAS_EXP>
-cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol, const double *d_trial, long long n,
+cudaError_t launch_delta_t(tr_ctx *ctx, const DevSystem &dsys, const double *d_sites, const int *d_mol, const double *d_trial, long long n,
                            double *d_es, double *d_ee, double *d_de)
 {
     auto kern = delta_energy_kernel<L, W, SPL, HAS_EXP>;
@@ -173,7 +198,7 @@ cudaError_t launch_delta_t(tr_ctx *ctx, const double *d_sites, const int *d_mol,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)(n < 4096 ? n : 4096);
-    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(ctx->sys, d_sites, d_mol, d_trial, n, d_es, d_ee, d_de);
+    kern<<<blocks, Team<L, W>::TPC, smem, ctx->stream>>>(dsys, d_sites, d_mol, d_trial, n, d_es, d_ee, d_de);
     return cudaGetLastError();
 }
 
@@ -219,15 +244,27 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
     // 65..192 sites the warp-per-chain team kernel is ahead (0.55 vs 0.45 G moves/s on (NH4Cl)32); tr_set_kernel overrides
     ctx->use_crew = ctx->threads_per_chain == 0 && v.W == 1 && ctx->kernel_choice != TR_KERNEL_TEAM &&
                     (v.L == 16 || ctx->kernel_choice == TR_KERNEL_CREW);
-    if (int r = prepare_variant(ctx, v)) return r;
+    // up to TR_CREW2_MAX_MOL particles the particle-major kernel with the pair-energy cache takes over (crew2.cuh)
+    ctx->use_crew2 = ctx->threads_per_chain == 0 && (ctx->kernel_choice == TR_KERNEL_AUTO || ctx->kernel_choice == TR_KERNEL_CREW2) &&
+                     crew2_pick(ctx, max_mol_sites_of(ctx), &ctx->crew2);
+    NEED(ctx, ctx->use_crew2 || ctx->kernel_choice != TR_KERNEL_CREW2, "Error: no crew2 kernel variant for this system (%d particles, %d sites in the largest)",
+         ctx->sys.n_mol, max_mol_sites_of(ctx));
+    if (ctx->use_crew2) {
+        ctx->use_crew = false;
+        const Crew2Variant &c2 = ctx->crew2;
+        if (int r = prepare_tables(ctx, ctx->run_tabs, 1, Variant{c2.L, c2.M, c2.SS}, c2.L * c2.M * c2.SS, &ctx->run_sys)) return r;
+    } else if (int r = prepare_variant(ctx, ctx->run_tabs, v, &ctx->run_sys)) return r;
     {
         char nm[96];
-        if (ctx->use_crew) snprintf(nm, sizeof nm, "crew_kernel<L=%d,SPL=%d>", v.L, v.SPL);
+        if (ctx->use_crew2) snprintf(nm, sizeof nm, "crew2_kernel<L=%d,M=%d,SS=%d>", ctx->crew2.L, ctx->crew2.M, ctx->crew2.SS);
+        else if (ctx->use_crew) snprintf(nm, sizeof nm, "crew_kernel<L=%d,SPL=%d>", v.L, v.SPL);
         else snprintf(nm, sizeof nm, "anneal_kernel<L=%d,W=%d,SPL=%d>", v.L, v.W, v.SPL);
         ctx->kernel_name = nm;
     }
-    int smem = 0;
-    if (ctx->use_crew) {
+    int smem = 0, tri = 0;
+    if (ctx->use_crew2) {
+        if (int r = crew2_smem_bytes(ctx, &smem, &tri)) return r;
+    } else if (ctx->use_crew) {
         if (int r = crew_smem_bytes(ctx, n_chains, &smem)) return r;
     } else {
         cudaError_t e;
@@ -268,6 +305,7 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
         CK(ctx, ctx->d_points.alloc(C * max_points));
         CK(ctx, cudaMemsetAsync(ctx->d_points.p, 0, C * max_points * sizeof(tr_point_rec), ctx->stream));
     } else ctx->d_points.release();
+    if (ctx->use_crew2) CK(ctx, ctx->d_pair_cache.alloc(C * (size_t)tri)); else ctx->d_pair_cache.release();
     if (ctx->trace_moves > 0) {
         CK(ctx, ctx->d_trace.alloc(C * (size_t)ctx->trace_moves));
         CK(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, C * (size_t)ctx->trace_moves * sizeof(tr_trace_rec), ctx->stream));
@@ -433,7 +471,7 @@ extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_system = false;
     ctx->n_chains = 0;
-    ctx->prepared = Variant{0, 0, 0};
+    ctx->run_tabs.layout = -1; ctx->probe_tabs.layout = -1;
     ctx->h_mol_off.assign(s->mol_site_off, s->mol_site_off + s->n_mol + 1);
     ctx->h_site_info = info;
     if (int r = upload(ctx, ctx->d_mol_off, s->mol_site_off, (size_t)s->n_mol + 1)) return r;
@@ -586,8 +624,8 @@ extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t fi
 extern "C" int tr_set_kernel(tr_ctx *ctx, int32_t kernel, int32_t chains_per_block, int32_t blocks_per_sm)
 {
     if (!ctx) return TR_EINVAL;
-    NEED(ctx, kernel == TR_KERNEL_AUTO || kernel == TR_KERNEL_TEAM || kernel == TR_KERNEL_CREW,
-         "Error: kernel must be TR_KERNEL_AUTO, TR_KERNEL_TEAM or TR_KERNEL_CREW");
+    NEED(ctx, kernel == TR_KERNEL_AUTO || kernel == TR_KERNEL_TEAM || kernel == TR_KERNEL_CREW || kernel == TR_KERNEL_CREW2,
+         "Error: kernel must be TR_KERNEL_AUTO, TR_KERNEL_TEAM, TR_KERNEL_CREW or TR_KERNEL_CREW2");
     NEED(ctx, chains_per_block >= 0 && chains_per_block <= 32 && blocks_per_sm >= 0 && blocks_per_sm <= 8,
          "Error: chains_per_block must be 0..32 and blocks_per_sm 0..8");
     ctx->kernel_choice = kernel;
@@ -625,7 +663,8 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     if (int r = need_chains(ctx)) return r;
     const Variant v = ctx->variant;
     KParams P{};
-    P.sys = ctx->sys;
+    P.sys = ctx->run_sys;
+    P.pair_cache = ctx->d_pair_cache.p;
     P.sched = ctx->d_sched.p;
     P.ctrl = ctx->d_ctrl.p;
     P.sites = ctx->d_sites.p;
@@ -643,7 +682,9 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     P.max_points = ctx->max_points;
     P.max_snaps = ctx->max_snaps;
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->use_crew) {
+    if (ctx->use_crew2) {
+        if (int r = launch_crew2(ctx, P)) return r;
+    } else if (ctx->use_crew) {
         if (int r = launch_crew(ctx, P)) return r;
     } else {
         cudaError_t e;
@@ -880,16 +921,15 @@ extern "C" int tr_total_energy(tr_ctx *ctx, const double *sites, int64_t n, doub
     NEED(ctx, sites && energy && n > 0, "Error: tr_total_energy: bad arguments");
     Variant v;
     if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v)) return fail(ctx, TR_ELIMIT, "Error: system too large");
-    NEED(ctx, ctx->n_chains == 0 || same_variant(v, ctx->variant),
-         "Error: threads_per_chain changed while chains are live; re-initialise the chains first");
-    if (int r = prepare_variant(ctx, v)) return r;
+    DevSystem dsys;
+    if (int r = prepare_variant(ctx, ctx->probe_tabs, v, &dsys)) return r;
     DevBuf<double> d_sites, d_out;
     const size_t S3 = (size_t)ctx->sys.n_sites * 3;
     CK(ctx, d_sites.alloc((size_t)n * S3));
     CK(ctx, d_out.alloc((size_t)n));
     CK(ctx, cudaMemcpyAsync(d_sites.p, sites, (size_t)n * S3 * 8, cudaMemcpyHostToDevice, ctx->stream));
     cudaError_t e;
-#define CALL_TOTAL(L, W, SPL, HE) launch_total_t<L, W, SPL, HE>(ctx, d_sites.p, n, d_out.p)
+#define CALL_TOTAL(L, W, SPL, HE) launch_total_t<L, W, SPL, HE>(ctx, dsys, d_sites.p, n, d_out.p)
     TR_DISPATCH(v, ctx->sys.has_exp, CALL_TOTAL);
 #undef CALL_TOTAL
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: total-energy kernel launch failed: %s", cudaGetErrorString(e));
@@ -909,9 +949,8 @@ extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *
     for (int64_t i = 0; i < n; i++) NEED(ctx, mol[i] >= 0 && mol[i] < ctx->sys.n_mol, "Error: mol[%lld] out of range", (long long)i);
     Variant v;
     if (!pick_variant(ctx, ctx->sys.n_sites, ctx->threads_per_chain, &v)) return fail(ctx, TR_ELIMIT, "Error: system too large");
-    NEED(ctx, ctx->n_chains == 0 || same_variant(v, ctx->variant),
-         "Error: threads_per_chain changed while chains are live; re-initialise the chains first");
-    if (int r = prepare_variant(ctx, v)) return r;
+    DevSystem dsys;
+    if (int r = prepare_variant(ctx, ctx->probe_tabs, v, &dsys)) return r;
     DevBuf<double> d_sites, d_trial, d_es, d_ee, d_de;
     DevBuf<int> d_mol;
     const size_t S3 = (size_t)ctx->sys.n_sites * 3, T3 = (size_t)TR_MAX_MOL_SITES * 3;
@@ -925,7 +964,7 @@ extern "C" int tr_delta_energy(tr_ctx *ctx, const double *sites, const int32_t *
     CK(ctx, cudaMemcpyAsync(d_trial.p, trial, (size_t)n * T3 * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d_mol.p, mol, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     cudaError_t e;
-#define CALL_DELTA(L, W, SPL, HE) launch_delta_t<L, W, SPL, HE>(ctx, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, d_de.p)
+#define CALL_DELTA(L, W, SPL, HE) launch_delta_t<L, W, SPL, HE>(ctx, dsys, d_sites.p, d_mol.p, d_trial.p, n, d_es.p, d_ee.p, d_de.p)
     TR_DISPATCH(v, ctx->sys.has_exp, CALL_DELTA);
 #undef CALL_DELTA
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: delta-energy kernel launch failed: %s", cudaGetErrorString(e));
