@@ -103,6 +103,14 @@ struct __align__(16) CrewChain {
 // evaluated the move (PLAN_AUTO) and in the chain's control lane (bookkeeping): same inputs, same code, same bits.
 // rand > exp(-dE / kT)  <=>  dE > -kT log(rand) is decided on the pre-computed threshold when dE is away from the
 // rounding noise of either form, else by the reference's own expression.
+// The reference's own expression, rand > Math.pow(Math.E, -dE / (kB T)) (Space.java:683-687); out of line: it is only needed
+// inside the guard band and when no threshold was prepared, and the hot loops have to stay small (instruction cache).
+static __device__ __noinline__ int crew_metropolis_exact(double dE, double kBt, double rnd)
+{
+    const double test = exp(__ddiv_rn(__dmul_rn(-1.0, dE), kBt));
+    return rnd > test ? 0 : 1;
+}
+
 __device__ __forceinline__ void crew_metropolis(int oob, double dE, bool tzero, bool metro_ok, double rnd, double thr, double grd,
                                                 double kBt, int &acc, int &drew)
 {
@@ -112,10 +120,7 @@ __device__ __forceinline__ void crew_metropolis(int oob, double dE, bool tzero, 
         if (tzero) acc = 0;
         else if (metro_ok && dE > thr + grd) acc = 0;
         else if (metro_ok && dE < thr - grd) acc = 1;
-        else {
-            const double test = exp(__ddiv_rn(__dmul_rn(-1.0, dE), kBt));
-            if (rnd > test) acc = 0;
-        }
+        else acc = crew_metropolis_exact(dE, kBt, rnd);
     }
 }
 

@@ -1,5 +1,5 @@
-// The annealing hot path, second warp-specialised kernel ("crew2"): molecule-major energy teams, a per-chain cache of
-// particle-pair energies, and the control flow split over two control warps.  Same reference code as crew.cuh:
+// The annealing hot path, second warp-specialised kernel ("crew2"): particle-major energy teams, a per-chain cache of
+// particle-pair energies, and the control flow split over three control warps.  Same reference code as crew.cuh:
 // Main.sawtoothAnneal (Main.java:177-263), Space.move / Space.rotate (Space.java:660-734), Molecule.rotateTemp
 // (Molecule.java:64-97), Atom.calcEnergy (Atom.java:91-119), Space.calcEnergy (Space.java:648-658).
 //
@@ -15,16 +15,18 @@
 //     resumed runs bit-identical.  A rejected rotation still applies Molecule.rotateTemp's (a.x - x) + x round trip to the
 //     committed coordinates (Molecule.java:70-72,90-92): cached entries of that particle then describe coordinates that
 //     differ by at most one ulp, once (the round trip is idempotent) - far below the rounding of the sums themselves.
-//   * MOLECULE-MAJOR TEAMS.  A team is L = 8 (or 16) lanes; lane l owns the particles l, l + L, l + 2L ... (M per lane,
-//     SS site slots each), so the per-neighbour energies the cache needs are plain per-lane sums, dE is reduced from
-//     per-neighbour differences e_new(n) - E(m, n) (less cancellation than differencing two large sums), and with L = 8
-//     one energy warp serves FOUR chains: the per-round overhead (plan, commit, geometry, staging, ring window,
-//     reduction, barrier) is paid once per four moves.
-//   * TWO CONTROL WARPS.  The control lane of crew.cuh needed 2 200 - 4 000 cycles per round; with the teams twice as
-//     fast it would be the critical path.  C1 keeps the S stream and the bookkeeping (settle, accumulators, picks,
-//     translation vectors, modes); C2 owns everything transcendental: the rotation draw (R stream, sincos) and the
-//     Metropolis threshold -kT log(rand).  C2 needs nothing C1 computes in the same round: it learns which move is in flight
-//     from the plan C1 posted a round earlier and from the sign of the previous dE.
+//   * PARTICLE-MAJOR TEAMS.  A team is L = 8 lanes; lane l owns the particles l, l + L, l + 2L ... (M per lane, SS site
+//     slots each), so the per-neighbour energies the cache needs are plain per-lane sums, dE is reduced from
+//     per-neighbour differences e_new(n) - E(m, n) (less cancellation than differencing two large sums), and one energy
+//     warp serves FOUR chains: the per-round overhead (plan, commit, geometry, staging, reduction, barrier) is paid once
+//     per four moves.  The staged sites of the moved particle sit in registers for the whole evaluation.
+//   * THREE CONTROL WARPS, lane c <-> chain c.  The single control lane of crew.cuh needed 2 200 - 4 000 cycles per round;
+//     with the teams faster it would be the critical path.  C1 keeps the S stream and the bookkeeping (settle, accumulators,
+//     picks, translation vectors, modes).  C2 owns everything transcendental: the rotation draw (R stream, sincos) and the
+//     Metropolis threshold -kT log(rand); it needs nothing C1 computes in the same round (which move is in flight follows
+//     from the plan C1 posted a round earlier and from the sign of the previous dE).  C3 is the random-number generator:
+//     it keeps the three MT19937 streams' 128-word rings of tempered words topped up behind the consumers' cursors, four
+//     words at a time - the energy warps no longer spend a sixth of their instructions on ring windows.
 // One named barrier per round over all warps; plans and results are double-buffered by round parity.
 #pragma once
 #include "crew.cuh"
@@ -33,12 +35,15 @@ namespace tr {
 
 #ifdef TR_CREW_TIMING
 #define C2TM(...) __VA_ARGS__
+// ordered against the barrier (asm volatile with a memory clobber), unlike clock64()
+__device__ __forceinline__ long long c2_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 #else
 #define C2TM(...)
 #endif
 
 constexpr int C2_RING_NEED_M = 4;      // M words a move consumes, always (Main.java:199-208)
 constexpr int C2_RING_NEED_R = 8;      // R words guaranteed before a move is posted: angle double + up to 6 nextInt(3) tries
+constexpr int C2_MAX_BUBBLES = 256;    // rounds a chain may wait for random words before it is abandoned (CHAIN_ABORT_RNG)
 
 struct __align__(16) C2Cand {          // one drawn move, the S-stream part (Space.randMolecule + the translation vector)
     double va, vb, vc;
@@ -49,9 +54,9 @@ struct __align__(16) C2Cand {          // one drawn move, the S-stream part (Spa
 struct __align__(16) C2Plan {
     // ---- written by control warp C1
     C2Cand cand[2];                    // PLAN_AUTO: successor if no Metropolis double was drawn / if one was; PLAN_MOVE: cand[0]
-    int mode, flags, refill, snap_slot;
-    int movie_slot, endS0, endS1, pad0_;     // endS: S-ring position after each candidate's own draws (where its Metropolis double sits)
-    double kBt, pad1_;
+    int mode, flags, snap_slot, movie_slot;
+    int endS0, endS1;                  // S-ring position after each candidate's own draws (where its Metropolis double sits)
+    double kBt;
     // ---- written by control warp C2
     double rnd, thr;                   // Metropolis double of the move evaluated in the PREVIOUS round, -kT log(rnd)
     double grd, sn;                    // its guard band; sin of this round's rotation angle
@@ -65,22 +70,25 @@ struct __align__(16) C2Stage {         // one site of the moved particle at its 
     int pad_[2];
 };
 
+// Control region of a chain (what the control lanes touch); the team region (stage, com, coordinates, pair cache) is
+// separate so that each can have the stride that keeps its accesses off each other's banks.
 struct __align__(16) C2Chain {
     ChainCtrl ctrl;
     tr_schedule sch;
     uint32_t *mt;                      // global: [3][2][624] ping-pong blocks of this chain
-    uint32_t ring[3][CREW_RING];
+    __align__(16) uint32_t ring[3][CREW_RING];     // (C3 appends four words with one 16-byte store)
     C2Plan plan[2];
     CrewResult result[2];
     double etot;
     double bound;
-    int rd[3];
+    int rd[3];                         // ring words consumed so far (C1 -> C3)
     int pad0_;
-    int wr[3];
+    int wr[3];                         // ring words appended so far (C3 -> C1)
     int pad1_;
+    __align__(16) uint32_t pre[4][12]; // C3: operands of the next chunk of S, S + 1, M, R, copied in asynchronously (cp.async)
 };
 
-// Chain-independent tables at compile-time offsets; the chain regions follow at a runtime stride.
+// Chain-independent tables at compile-time offsets; the chain regions follow at runtime strides.
 template <int L, int M, int SS>
 struct C2Tables {
     static constexpr int SPL = M * SS;                 // site slots per lane
@@ -94,11 +102,13 @@ struct C2Tables {
 
     __host__ __device__ static int table_bytes(int n_types, bool has_exp) { return (OFF_CD + n_types * (n_types + 1) * 16 * (has_exp ? 2 : 1) + 127) & ~127; }
     __host__ __device__ static int tri_count(int n_mol) { return (n_mol * (n_mol - 1) / 2 + 1) & ~1; }
-    // chain region: fixed part, stage, com, coordinates, cache; padded to 64 mod 128 bytes so that the two teams a
-    // 64-bit shared-memory access serves in one pass (8 lanes x 8 bytes each) fall into different banks
-    __host__ __device__ static int chain_bytes(int n_mol)
+    // control region: 16 mod 128 bytes, so that the lanes of a control warp (one chain each) spread over the banks
+    __host__ __device__ static constexpr int ctrl_bytes() { return ((align16((int)sizeof(C2Chain)) + 127) & ~127) + 16; }
+    // team region: 64 mod 128 bytes, so that the two teams a 64-bit access serves in one pass (8 lanes x 8 bytes each) fall
+    // into different banks
+    __host__ __device__ static int team_bytes(int n_mol)
     {
-        int b = align16((int)sizeof(C2Chain)) + SS * (int)sizeof(C2Stage) + align16(n_mol * 24) + NPOS * 24 + tri_count(n_mol) * 8;
+        int b = SS * (int)sizeof(C2Stage) + align16(n_mol * 24) + NPOS * 24 + NMOL * 8 + tri_count(n_mol) * 8;
         b = (b + 127) & ~127;
         return b + 64;
     }
@@ -140,145 +150,173 @@ struct C2Tables {
 struct C2View {
     C2Chain *cs;
     C2Stage *stage;
-    double *com, *xs, *ys, *zs, *cache;
+    double *com, *xs, *ys, *zs, *cache, *pend;
 };
 
+// Block layout: tables | C control regions | C team regions
 template <int L, int M, int SS>
-__device__ __forceinline__ C2View c2_view(unsigned char *chains, int c, int stride, int n_mol)
+__device__ __forceinline__ C2View c2_view(unsigned char *chains, int c, int C, int n_mol)
 {
+    using TL = C2Tables<L, M, SS>;
     constexpr int NPOS = L * M * SS;
-    unsigned char *b = chains + (size_t)c * stride;
     C2View v;
-    v.cs = (C2Chain *)b;
-    b += align16((int)sizeof(C2Chain));
+    v.cs = (C2Chain *)(chains + (size_t)c * TL::ctrl_bytes());
+    unsigned char *b = chains + (size_t)C * TL::ctrl_bytes() + (size_t)c * TL::team_bytes(n_mol);
     v.stage = (C2Stage *)b;
     b += SS * (int)sizeof(C2Stage);
     v.com = (double *)b;
     b += align16(n_mol * 24);
     v.xs = (double *)b; v.ys = v.xs + NPOS; v.zs = v.ys + NPOS;
-    v.cache = v.zs + NPOS;
+    v.pend = v.zs + NPOS;                          // [M][L]: per-neighbour energies of the move staged last
+    v.cache = v.pend + L * M;
     return v;
 }
 
 __device__ __forceinline__ int tri_index(int lo, int hi) { return ((hi * (hi - 1)) >> 1) + lo; }
 
-// ---- ring upkeep (the three streams' windows), as in crew.cuh but on C2Chain ------------------------------------------
+// ---- C3: the random-number generator ------------------------------------------------------------------------------------------
+// One lane keeps one chain's three streams.  The 624-word blocks live in global memory (L2 / L1) in two ping-pong buffers
+// (mt19937.cuh): new[k] = (k < 227 ? old[k+397] : new[k-227]) ^ twist(old[k], k == 623 ? new[0] : old[k+1]).  Tempered words are
+// appended to the stream's 128-word ring in shared memory four at a time; the ring's write position is always a multiple of 4.
 
-template <int L>
-__device__ __forceinline__ CrewWindow<L> c2_ring_begin(C2Chain *cs, int s, int tl)
+struct C2Gen {                       // one stream as its generator lane sees it
+    uint32_t *mt;                    // global: [2][624]
+    uint32_t *ring;                  // shared: [CREW_RING]
+    int par, gen, fed;               // MtCursor
+    int wr;                          // words appended so far
+};
+
+// One word, whatever the state (used until the stream position is a multiple of 4: imported / rewound cursors).
+__device__ __forceinline__ void c2_gen_word(C2Gen &g)
 {
-    CrewWindow<L> w;
-    w.s = s > 2 ? -1 : s;
-    w.par = w.gen = w.fed = w.count = w.load = w.wr = 0;
-#pragma unroll
-    for (int j = 0; j < 32 / L; j++) w.a[j] = w.b[j] = w.far[j] = 0u;
-    if (w.s < 0) return w;
-    const MtCursor cur = cs->ctrl.rng[s];
-    uint32_t *mt = cs->mt + s * 2 * MT_N;
-    int par = cur.par, gen = cur.gen, fed = cur.fed;
-    if (fed >= MT_N) { par ^= 1; gen = 0; fed = 0; }
-    const uint32_t *B = mt + par * MT_N, *O = mt + (par ^ 1) * MT_N;
-    w.load = fed < gen;
-    const int limit = w.load ? gen : MT_N;
-    w.count = (limit - fed < 32) ? limit - fed : 32;
-    w.par = par; w.gen = gen; w.fed = fed; w.wr = cs->wr[s];
-#pragma unroll
-    for (int j = 0; j < 32 / L; j++) {
-        const int i = tl + j * L;
-        if (i < w.count) {
-            const int k = fed + i;
-            if (w.load) w.a[j] = B[k];
-            else {
-                w.a[j] = O[k];
-                w.b[j] = (k == MT_N - 1) ? B[0] : O[k + 1];
-                w.far[j] = (k < MT_N - MT_M) ? O[k + MT_M] : B[k + MT_M - MT_N];
-            }
-        }
+    if (g.fed >= MT_N) { g.par ^= 1; g.gen = 0; g.fed = 0; }
+    uint32_t *B = g.mt + g.par * MT_N;
+    const uint32_t *O = g.mt + (g.par ^ 1) * MT_N;
+    const int k = g.fed;
+    uint32_t v;
+    if (k < g.gen) v = B[k];
+    else {
+        const uint32_t a = O[k];
+        const uint32_t b = (k == MT_N - 1) ? B[0] : O[k + 1];
+        const uint32_t far = (k < MT_N - MT_M) ? O[k + MT_M] : B[k + MT_M - MT_N];
+        const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+        v = far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        B[k] = v;
+        g.gen = k + 1;
     }
-    return w;
+    g.ring[g.wr & (CREW_RING - 1)] = mt_temper(v);
+    g.fed = k + 1;
+    g.wr += 1;
 }
 
-template <int L>
-__device__ __forceinline__ void c2_ring_end(C2Chain *cs, const CrewWindow<L> &w, int tl, unsigned mask)
+// An aligned chunk of four words in two steps a round apart, so that C3 never waits for global memory: c2_chunk_issue starts
+// asynchronous copies (cp.async) of the chunk's operands into the chain's staging area and moves the ISSUE cursor;
+// c2_chunk_finish (next round or later, when the ring has room) twists, stores the new state words, tempers and appends.
+// A chunk's operands never depend on the chunks still in flight ahead of it: it reads old[k .. k+4], old[k+397 ..] or
+// new[k-227 ..] and (the last one of a block) new[0] - all at least 56 chunks old.
+struct C2Issue {                     // where the next chunk to be ISSUED sits (runs ahead of C2Gen by the chunks in flight)
+    int par, gen, fed;
+};
+
+__device__ __forceinline__ void c2_cp_async4(uint32_t *dst_smem, const uint32_t *src)
 {
-    if (w.s < 0) return;
-    uint32_t *mt = cs->mt + w.s * 2 * MT_N;
-#pragma unroll
-    for (int j = 0; j < 32 / L; j++) {
-        const int i = tl + j * L;
-        if (i < w.count) {
-            uint32_t v = w.a[j];
-            if (!w.load) {
-                const uint32_t y = (w.a[j] & 0x80000000u) | (w.b[j] & 0x7fffffffu);
-                v = w.far[j] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-                mt[w.par * MT_N + w.fed + i] = v;
-            }
-            cs->ring[w.s][(w.wr + i) & (CREW_RING - 1)] = mt_temper(v);
-        }
-    }
-    __syncwarp(mask);
-    if (tl == 0) {
-        MtCursor c;
-        c.par = w.par; c.gen = w.load ? w.gen : w.fed + w.count; c.fed = w.fed + w.count;
-        cs->ctrl.rng[w.s] = c;
-        __threadfence_block();                          // the control lanes read ahead as soon as they see the new cursor
-        cs->wr[w.s] = w.wr + w.count;
-    }
-    __syncwarp(mask);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void c2_cp_async16(uint32_t *dst_smem, const uint32_t *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
 
-template <int L>
-__device__ __forceinline__ void c2_ring_fill(C2Chain *cs, int tl, unsigned mask)
+// slot layout: [0..3] old[k..k+3] (or the words themselves: reload), [4] old[k+4] / new[0], [5..8] far words, [9] = 1: reload
+__device__ __forceinline__ void c2_chunk_issue(uint32_t *mt, C2Issue &it, uint32_t *slot)
 {
-    for (int s = 0; s < 3; s++) {
-        while (cs->wr[s] - cs->rd[s] <= CREW_RING_LOW) {
-            const CrewWindow<L> w = c2_ring_begin<L>(cs, s, tl);
-            c2_ring_end<L>(cs, w, tl, mask);
-        }
+    if (it.fed >= MT_N) { it.par ^= 1; it.gen = 0; it.fed = 0; }
+    uint32_t *B = mt + it.par * MT_N;
+    const uint32_t *O = mt + (it.par ^ 1) * MT_N;
+    const int k = it.fed;
+    if (k < it.gen) {                                          // (gen is a multiple of 4 whenever fed is)
+        c2_cp_async16(slot, B + k);
+        slot[9] = 1u;
+    } else {
+        c2_cp_async16(slot, O + k);
+        c2_cp_async4(slot + 4, (k + 4 == MT_N) ? B : O + k + 4);
+#pragma unroll
+        for (int i = 0; i < 4; i++) c2_cp_async4(slot + 5 + i, (k + i < MT_N - MT_M) ? O + k + i + MT_M : B + k + i + MT_M - MT_N);
+        slot[9] = 0u;
+        it.gen = k + 4;
     }
+    it.fed = k + 4;
+}
+
+__device__ __forceinline__ void c2_chunk_finish(C2Gen &g, const uint32_t *slot)
+{
+    if (g.fed >= MT_N) { g.par ^= 1; g.gen = 0; g.fed = 0; }
+    const int k = g.fed;
+    const uint4 a = *(const uint4 *)slot;
+    uint4 v = a;
+    if (slot[9] == 0u) {
+        const uint32_t a4 = slot[4];
+        const uint4 f = make_uint4(slot[5], slot[6], slot[7], slot[8]);
+        uint32_t y;
+        y = (a.x & 0x80000000u) | (a.y & 0x7fffffffu); v.x = f.x ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        y = (a.y & 0x80000000u) | (a.z & 0x7fffffffu); v.y = f.y ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        y = (a.z & 0x80000000u) | (a.w & 0x7fffffffu); v.z = f.z ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        y = (a.w & 0x80000000u) | (a4 & 0x7fffffffu);  v.w = f.w ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        *(uint4 *)(g.mt + g.par * MT_N + k) = v;
+        g.gen = k + 4;
+    }
+    g.ring[g.wr & (CREW_RING - 1)] = mt_temper(v.x);
+    g.ring[(g.wr + 1) & (CREW_RING - 1)] = mt_temper(v.y);
+    g.ring[(g.wr + 2) & (CREW_RING - 1)] = mt_temper(v.z);
+    g.ring[(g.wr + 3) & (CREW_RING - 1)] = mt_temper(v.w);
+    g.fed = k + 4;
+    g.wr += 4;
 }
 
 // ---- energy -------------------------------------------------------------------------------------------------------------
 
-// One staged site (trial position) against the SS site slots of ONE particle slot of this lane: SS evaluations written
+// One staged site (trial position) against the SS site slots of one particle slot of this lane: SS evaluations written
 // operation by operation across the group (independent dependency chains for the 8-cycle FP64 latency), summed into e.
-// MODE 0: Coulomb only; 1: + Lennard-Jones on the slots named by `ljb`; 2: + Born-Mayer on every slot.
-template <int SS, int MODE>
-__device__ __forceinline__ double c2_group(const C2Stage &st, const unsigned char *tab_cd, const unsigned char *tab_ab, const double *x, const double *y,
-                                           const double *z, const double *qm, const int *col, unsigned ljb, double e)
+// `lj`: the staged site carries Lennard-Jones parameters in some team of the warp (warp-uniform); then the site slots named by
+// `ljb` add the r^-6 / r^-12 terms (every slot, with the Born-Mayer term, when HAS_EXP).
+template <int SS, bool HAS_EXP>
+__device__ __forceinline__ double c2_site(double nx, double ny, double nz, double kq, int row, bool lj, const unsigned char *tab_cd,
+                                          const unsigned char *tab_ab, const double *x, const double *y, const double *z, const double *q,
+                                          const int *info, unsigned ljb, double e)
 {
     double r2[SS], y0[SS], t[SS], u[SS], p[SS], ri[SS];
 #pragma unroll
-    for (int b = 0; b < SS; b++) { const double d = x[b] - st.nx; r2[b] = d * d; }
+    for (int j = 0; j < SS; j++) { const double d = x[j] - nx; r2[j] = d * d; }
 #pragma unroll
-    for (int b = 0; b < SS; b++) { const double d = y[b] - st.ny; r2[b] = fma(d, d, r2[b]); }
+    for (int j = 0; j < SS; j++) { const double d = y[j] - ny; r2[j] = fma(d, d, r2[j]); }
 #pragma unroll
-    for (int b = 0; b < SS; b++) { const double d = z[b] - st.nz; r2[b] = fma(d, d, r2[b]); }
+    for (int j = 0; j < SS; j++) { const double d = z[j] - nz; r2[j] = fma(d, d, r2[j]); }
 #pragma unroll
-    for (int b = 0; b < SS; b++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[b]) : "d"(r2[b]));
+    for (int j = 0; j < SS; j++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[j]) : "d"(r2[j]));
 #pragma unroll
-    for (int b = 0; b < SS; b++) t[b] = r2[b] * y0[b];
+    for (int j = 0; j < SS; j++) t[j] = r2[j] * y0[j];
 #pragma unroll
-    for (int b = 0; b < SS; b++) u[b] = fma(-t[b], y0[b], 1.0);
+    for (int j = 0; j < SS; j++) u[j] = fma(-t[j], y0[j], 1.0);
 #pragma unroll
-    for (int b = 0; b < SS; b++) p[b] = fma(u[b], 0.375, 0.5);
+    for (int j = 0; j < SS; j++) p[j] = fma(u[j], 0.375, 0.5);
 #pragma unroll
-    for (int b = 0; b < SS; b++) u[b] = y0[b] * u[b];
+    for (int j = 0; j < SS; j++) u[j] = y0[j] * u[j];
 #pragma unroll
-    for (int b = 0; b < SS; b++) ri[b] = fma(p[b], u[b], y0[b]);
+    for (int j = 0; j < SS; j++) ri[j] = fma(p[j], u[j], y0[j]);
 #pragma unroll
-    for (int b = 0; b < SS; b++) e = fma(st.kq * qm[b], ri[b], e);
-    if (MODE >= 1) {
+    for (int j = 0; j < SS; j++) e = fma(kq * q[j], ri[j], e);
+    if (HAS_EXP || lj) {
 #pragma unroll
-        for (int b = 0; b < SS; b++) {
-            if (MODE >= 2 || ((ljb >> b) & 1u)) {
-                const double2 cd = *(const double2 *)(tab_cd + st.row + col[b]);
-                const double i2 = ri[b] * ri[b];
+        for (int j = 0; j < SS; j++) {
+            if (HAS_EXP || ((ljb >> j) & 1u)) {
+                const int cj = info_col(info[j]);
+                const double2 cd = *(const double2 *)(tab_cd + row + cj);
+                const double i2 = ri[j] * ri[j];
                 const double i6 = i2 * i2 * i2;
                 e = fma(fma(cd.y, i6, -cd.x), i6, e);                  // + D/r^12 - C/r^6
-                if (MODE >= 2) {
-                    const double2 ab = *(const double2 *)(tab_ab + st.row + col[b]);
-                    e = fma(ab.x, exp(-ab.y * (r2[b] * ri[b])), e);
+                if (HAS_EXP) {
+                    const double2 ab = *(const double2 *)(tab_ab + row + cj);
+                    e = fma(ab.x, exp(-ab.y * (r2[j] * ri[j])), e);
                 }
             }
         }
@@ -286,28 +324,27 @@ __device__ __forceinline__ double c2_group(const C2Stage &st, const unsigned cha
     return e;
 }
 
-// What a team keeps in registers between rounds to commit the move it staged last (setTemps, Molecule.java:128-135).
-template <int M>
+// What a team keeps in registers between rounds to commit the move it staged last (setTemps, Molecule.java:128-135); the
+// per-neighbour energies at the trial position wait in the team's shared-memory region (C2View::pend).
 struct C2Pending {
     double tx, ty, tz;         // lane a < s_m: trial coordinates of site a
     double cx, cy, cz;         // lane 0: the particle's centre of mass if the move is committed
-    double e[M];               // per-neighbour energies at the trial position (what the cache takes)
-    int cidx[M];               // their cache slots, or -1
     int pp;                    // position of this lane's staged site, or -1
     int pm;                    // lane 0: particle whose centre of mass moves, or -1 (rotation)
+    int m;                     // the moved particle
 };
 
-// One posted move for one chain, one team (Space.java:660-734 after the draws): trial geometry with the 0.75 * spaceLen box
-// test, per-neighbour energies at the trial position, dE against the cached energies.
-template <int L, int M, int SS, bool HAS_EXP, bool TRACE>
-__device__ __forceinline__ void c2_move(const unsigned char *smem, const C2View &v, const DevSystem &sys, const C2Cand &d, const C2Plan *pl,
-                                        unsigned ljb, int tl, unsigned mask, CrewResult *res, C2Pending<M> &pend, double &dE_out, int &oob_out)
+// Trial geometry of a posted move (Space.java:660-667 / 692-710 after the draws): lane a < s_m builds site a of particle m at
+// its trial position and stages it; returns this lane's box-test result (0.75 * spaceLen, Space.java:663,706).
+template <int L, int M, int SS>
+__device__ __forceinline__ bool c2_geometry(const unsigned char *smem, const C2View &v, const DevSystem &sys, const C2Cand &d, const C2Plan *pl, int tl,
+                                            C2Pending &pend, int &lj_out)
 {
     using TL = C2Tables<L, M, SS>;
-    C2Chain *cs = v.cs;
     const int m = d.m, sm = d.info & 0xff, rot = (d.info >> 8) & 1;
     bool oob = false;
-    pend.pp = -1;
+    pend.pp = -1; pend.m = m;
+    lj_out = 0;
     if (tl < sm) {
         const int p = TL::pos_of(m, tl);
         const int inf = TL::pos_info(smem, p);
@@ -318,19 +355,16 @@ __device__ __forceinline__ void c2_move(const unsigned char *smem, const C2View 
             const double va = pl->sn, vb = pl->cs, nsn = __dmul_rn(-1.0, va);
             const int axis = pl->axis;
             const double ax = __dsub_rn(ox, cx), ay = __dsub_rn(oy, cy), az = __dsub_rn(oz, cz);
-            if (axis == 0) {
-                tx = ax;
-                ty = __dadd_rn(__dmul_rn(vb, ay), __dmul_rn(va, az));
-                tz = __dadd_rn(__dmul_rn(nsn, ay), __dmul_rn(vb, az));
-            } else if (axis == 1) {
-                tx = __dsub_rn(__dmul_rn(vb, ax), __dmul_rn(va, az));
-                ty = ay;
-                tz = __dadd_rn(__dmul_rn(va, ax), __dmul_rn(vb, az));
-            } else {
-                tx = __dadd_rn(__dmul_rn(vb, ax), __dmul_rn(va, ay));
-                ty = __dadd_rn(__dmul_rn(nsn, ax), __dmul_rn(vb, ay));
-                tz = az;
-            }
+            // The Givens rotation mixes two coordinates (pu, pw) and leaves the third alone.  Axis 0: (y, z), axis 1: (x, z),
+            // axis 2: (x, y); first result cos*pu + sin*pw (axis 1: cos*pu - sin*pw), second -sin*pu + cos*pw (axis 1:
+            // sin*pu + cos*pw) - selected, not branched, so that teams with different axes do not serialise.
+            const double pu = axis == 0 ? ay : ax, pw = axis == 2 ? ay : az;
+            const double s1 = axis == 1 ? nsn : va, s2 = axis == 1 ? va : nsn;
+            const double ru = __dadd_rn(__dmul_rn(vb, pu), __dmul_rn(s1, pw));
+            const double rw = __dadd_rn(__dmul_rn(s2, pu), __dmul_rn(vb, pw));
+            tx = axis == 0 ? ax : ru;
+            ty = axis == 0 ? ru : (axis == 1 ? ay : rw);
+            tz = axis == 2 ? az : rw;
             // a.x += x: the committed coordinate keeps the (a.x - x) + x round trip even if the move is rejected
             v.xs[p] = __dadd_rn(ax, cx); v.ys[p] = __dadd_rn(ay, cy); v.zs[p] = __dadd_rn(az, cz);
             tx = __dadd_rn(tx, cx); ty = __dadd_rn(ty, cy); tz = __dadd_rn(tz, cz);
@@ -343,7 +377,8 @@ __device__ __forceinline__ void c2_move(const unsigned char *smem, const C2View 
         st.row = info_type(inf) * sys.row_stride; st.lj = info_lj(inf);
         st.pad_[0] = st.pad_[1] = 0;
         v.stage[tl] = st;
-        const double b = cs->bound;                  // t > L*0.75 || t < L*-0.75; the lower bound is the exact negative
+        lj_out = st.lj;
+        const double b = v.cs->bound;                // t > L*0.75 || t < L*-0.75; the lower bound is the exact negative
         oob = (fabs(tx) > b) | (fabs(ty) > b) | (fabs(tz) > b);
         pend.tx = tx; pend.ty = ty; pend.tz = tz; pend.pp = p;
     }
@@ -355,60 +390,65 @@ __device__ __forceinline__ void c2_move(const unsigned char *smem, const C2View 
             pend.cz = __dadd_rn(v.com[3 * m + 2], d.vc);
         }
     }
-    const bool any_oob = (__ballot_sync(mask, oob) & mask) != 0u;      // (also orders the staging stores before the reads below)
-    __syncwarp(mask);
-    if (any_oob) {
-        if (tl == 0) res->oob = 1;
-        dE_out = 0.0; oob_out = 1;
-        return;
-    }
-    // This lane's particles, one particle slot at a time against every staged site.  m itself and empty slots are taken
-    // out by a far-away x, a zero charge and the all-zero table column (no r = 0, no branch).
+    return oob;
+}
+
+// Per-neighbour energies of the staged particle at its trial position against this lane's particles, and this lane's part of
+// eEnd - eStart (cached energies subtracted per neighbour).  `sm_w` / `ljw` are warp-uniform: the most staged sites any team of
+// the warp has this round, and which staged sites carry Lennard-Jones parameters in any team - a team with fewer staged sites
+// sees neutral entries (zero charge, far away), so the loop bounds and the arithmetic form never diverge inside a warp.
+// The slot that holds the moved particle itself (and empty slots) is evaluated like any other and discarded afterwards.
+// The loop over the particle slots is a real loop: the whole kernel's hot code has to stay inside the 32 KB instruction cache.
+template <int L, int M, int SS, bool HAS_EXP, bool TRACE>
+__device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2View &v, const DevSystem &sys, int m, int sm_w, unsigned ljw,
+                                            unsigned ljb, int tl, double &dl, double &sl, double &el)
+{
+    using TL = C2Tables<L, M, SS>;
     const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
     const int nmol = sys.n_mol;
-    double dl = 0.0, sl = 0.0, el = 0.0;
+    // the staged sites, in registers for the whole evaluation
+    double snx[SS], sny[SS], snz[SS], skq[SS];
+    int srow[SS];
 #pragma unroll
+    for (int a = 0; a < SS; a++) {
+        if (a < sm_w) {
+            const C2Stage st = v.stage[a];
+            snx[a] = st.nx; sny[a] = st.ny; snz[a] = st.nz; skq[a] = st.kq; srow[a] = st.row;
+        } else { snx[a] = sny[a] = snz[a] = skq[a] = 0.0; srow[a] = 0; }
+    }
+    dl = 0.0; sl = 0.0; el = 0.0;
+    const double *px = v.xs + tl, *py = v.ys + tl, *pz = v.zs + tl;
+    const double *pq = (const double *)(smem + TL::OFF_QPOS) + tl;
+    const int *pi = (const int *)(smem + TL::OFF_POS_INFO) + tl;
+    double *pe = v.pend + tl;
+#pragma unroll 1
     for (int k = 0; k < M; k++) {
+        double x[SS], y[SS], z[SS], q[SS];
+        int info[SS];
+#pragma unroll
+        for (int b = 0; b < SS; b++) {
+            x[b] = px[b * L]; y[b] = py[b * L]; z[b] = pz[b * L]; q[b] = pq[b * L];
+            info[b] = (HAS_EXP || ljw) ? pi[b * L] : 0;
+        }
+        double e = 0.0;
+#pragma unroll
+        for (int a = 0; a < SS; a++)
+            if (a < sm_w) e = c2_site<SS, HAS_EXP>(snx[a], sny[a], snz[a], skq[a], srow[a], ((ljw >> a) & 1u) != 0u, tab_cd, tab_ab, x, y, z, q, info, ljb, e);
         const int n = tl + L * k;
         const bool on = (n != m) & (n < nmol);
         const int lo = n < m ? n : m, hi = n < m ? m : n;
-        const int ci = on ? tri_index(lo, hi) : -1;
-        const double eold = on ? v.cache[on ? ci : 0] : 0.0;
-        double x[SS], y[SS], z[SS], qm[SS];
-        int cl[SS];
-#pragma unroll
-        for (int b = 0; b < SS; b++) {
-            const int p = (k * SS + b) * L + tl;
-            x[b] = on ? v.xs[p] : FAR_AWAY; y[b] = v.ys[p]; z[b] = v.zs[p];
-            qm[b] = on ? TL::qpos(smem, p) : 0.0;
-            cl[b] = on ? info_col(TL::pos_info(smem, p)) : sys.zero_col;
-        }
-        double e = 0.0;
-        for (int a = 0; a < sm; a++) {
-            const C2Stage st = v.stage[a];
-            if (HAS_EXP) e = c2_group<SS, 2>(st, tab_cd, tab_ab, x, y, z, qm, cl, ljb, e);
-            else if (st.lj) e = c2_group<SS, 1>(st, tab_cd, tab_ab, x, y, z, qm, cl, ljb, e);
-            else e = c2_group<SS, 0>(st, tab_cd, tab_ab, x, y, z, qm, cl, ljb, e);
-        }
-        pend.cidx[k] = ci;
-        pend.e[k] = e;
-        dl += e - eold;                                   // eEnd - eStart from per-neighbour differences
-        if (TRACE) { sl += eold; el += e; }
+        const double eold = v.cache[on ? tri_index(lo, hi) : 0];
+        *pe = e;                                              // waits for the commit
+        dl += on ? e - eold : 0.0;                            // eEnd - eStart from per-neighbour differences
+        if (TRACE) { sl += on ? eold : 0.0; el += on ? e : 0.0; }
+        px += SS * L; py += SS * L; pz += SS * L; pq += SS * L; pi += SS * L; pe += L;
     }
-    const double dE = crew_team_sum<L>(dl, mask);
-    if (TRACE) { sl = crew_team_sum<L>(sl, mask); el = crew_team_sum<L>(el, mask); }
-    if (tl == 0) {
-        res->oob = 0;
-        res->dE = dE;
-        if (TRACE) { res->eS = sl; res->eE = el; }
-    }
-    dE_out = dE; oob_out = 0;
 }
 
 // Space.calcEnergy (Space.java:648-658) of the committed structure, one team; every particle-pair energy is stored into
 // the cache on the way (this = the lower-indexed particle, as Space.calcEnergy has it).
 template <int L, int M, int SS, bool HAS_EXP>
-__device__ __noinline__ double c2_total_energy(const unsigned char *smem, const C2View &v, const DevSystem &sys, int tl, unsigned mask)
+__device__ __forceinline__ double c2_total_energy(const unsigned char *smem, const C2View &v, const DevSystem &sys, int tl, unsigned mask)
 {
     using TL = C2Tables<L, M, SS>;
     const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
@@ -462,6 +502,20 @@ __device__ __forceinline__ void c2_sites_to_global(const C2View &v, double *dst,
     }
 }
 
+// A Space.calcEnergy round (once per point): the energy for C1, the write(n) / writeMovie structure dumps.  Out of line: rare.
+template <int L, int M, int SS, bool HAS_EXP>
+__device__ __noinline__ void c2_total_round(const unsigned char *smem, const C2View &v, const KParams &P, long long chain, int snap_slot, int movie_slot,
+                                            int tl, unsigned mask)
+{
+    const DevSystem &sys = P.sys;
+    const double e = c2_total_energy<L, M, SS, HAS_EXP>(smem, v, sys, tl, mask);
+    if (tl == 0) v.cs->etot = e;
+    if (snap_slot >= 0)
+        c2_sites_to_global<L, M, SS>(v, P.snap_sites + ((size_t)chain * P.max_snaps + snap_slot) * (size_t)sys.n_sites * 3, sys, tl);
+    if (movie_slot >= 0)
+        c2_sites_to_global<L, M, SS>(v, P.movie_sites + ((size_t)chain * P.max_points + movie_slot) * (size_t)sys.n_sites * 3, sys, tl);
+}
+
 template <int L, int M, int SS>
 __device__ __forceinline__ void c2_sites_from_global(const C2View &v, const double *src, const DevSystem &sys, int tl)
 {
@@ -482,14 +536,18 @@ struct C2Pick {                      // the S-stream part of a move starting at 
     bool ok;
 };
 
+constexpr int C2_CTRL_WARPS = 3;
+
 template <int L, int M, int SS, bool HAS_EXP, bool TRACE, int EW>
-__global__ void __launch_bounds__(32 * (2 + EW), 1)
-crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
+__global__ void __launch_bounds__(32 * (C2_CTRL_WARPS + EW), 1)
+crew2_kernel(const __grid_constant__ KParams P, const int C)
 {
     using TL = C2Tables<L, M, SS>;
     constexpr int TPW = 32 / L;                    // chains an energy warp evaluates side by side
-    constexpr int NT = 32 * (2 + EW);
+    constexpr int NW = C2_CTRL_WARPS + EW;
+    constexpr int NT = 32 * NW;
     static_assert(EW * TPW <= 32, "one control lane per chain");
+    static_assert(SS <= L, "one lane per site of the moved particle");
     extern __shared__ __align__(16) unsigned char smem[];
     const DevSystem &sys = P.sys;
     TL::load(smem, sys);
@@ -504,10 +562,10 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
     const int ntri = TL::tri_count(sys.n_mol);
 
     // chain state -> shared memory (every team takes whole chains)
-    for (int c0 = warp * TPW; c0 < nloc; c0 += (2 + EW) * TPW) {
+    for (int c0 = warp * TPW; c0 < nloc; c0 += NW * TPW) {
         const int c = c0 + team;
         if (c < nloc) {
-            const C2View v = c2_view<L, M, SS>(chains, c, stride, sys.n_mol);
+            const C2View v = c2_view<L, M, SS>(chains, c, C, sys.n_mol);
             const long long ch = chain0 + c;
             const int *src = (const int *)(P.ctrl + ch);
             int *dst = (int *)&v.cs->ctrl;
@@ -526,18 +584,88 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
                 v.cs->bound = v.cs->ctrl.space_len * 0.75;
             }
             if (tl < 3) { v.cs->wr[tl] = 0; v.cs->rd[tl] = 0; }
-            __syncwarp(mask);
-            if (!v.cs->ctrl.done) c2_ring_fill<L>(v.cs, tl, mask);
         }
     }
     __syncthreads();
 
-    if (warp == 0) {
+    if (warp == 2) {
+        // ================================================================ control warp C3: the random-number generator
+        const bool mine = lane < nloc;
+        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, sys.n_mol);
+        C2Chain *cs = v.cs;
+        C2Gen gM, gS, gR;
+        auto open_stream = [&](C2Gen &g, int s) {
+            const MtCursor cur = cs->ctrl.rng[s];
+            g.mt = cs->mt + s * 2 * MT_N; g.ring = cs->ring[s];
+            g.par = cur.par; g.gen = cur.gen; g.fed = cur.fed; g.wr = 0;
+        };
+        open_stream(gM, STREAM_M); open_stream(gS, STREAM_S); open_stream(gR, STREAM_R);
+        const bool work = mine && !cs->ctrl.done;
+        // chunks in flight: slot 0, 1 = the next two chunks of S (a queue: slot qS is the older one), slot 2 = M, slot 3 = R
+        C2Issue iM, iS, iR;
+        int qS = 0;
+        if (work) {
+            // prologue: align every stream to a multiple of 4 words, fill every ring but its last 8 words, start the first copies
+            while (gM.fed & 3) c2_gen_word(gM);
+            while (gS.fed & 3) c2_gen_word(gS);
+            while (gR.fed & 3) c2_gen_word(gR);
+            iM.par = gM.par; iM.gen = gM.gen; iM.fed = gM.fed;
+            iS.par = gS.par; iS.gen = gS.gen; iS.fed = gS.fed;
+            iR.par = gR.par; iR.gen = gR.gen; iR.fed = gR.fed;
+#pragma unroll 1
+            for (int i = 0; i < CREW_RING / 4 - 2; i++) {
+                c2_chunk_issue(gM.mt, iM, cs->pre[2]); c2_chunk_issue(gS.mt, iS, cs->pre[0]); c2_chunk_issue(gR.mt, iR, cs->pre[3]);
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                c2_chunk_finish(gM, cs->pre[2]); c2_chunk_finish(gS, cs->pre[0]); c2_chunk_finish(gR, cs->pre[3]);
+            }
+            c2_chunk_issue(gS.mt, iS, cs->pre[0]); c2_chunk_issue(gS.mt, iS, cs->pre[1]);
+            c2_chunk_issue(gM.mt, iM, cs->pre[2]); c2_chunk_issue(gR.mt, iR, cs->pre[3]);
+            cs->wr[STREAM_M] = gM.wr; cs->wr[STREAM_S] = gS.wr; cs->wr[STREAM_R] = gR.wr;
+        }
+        __syncwarp();
+        crew_bar(NT);                                       // "rings filled"
+        C2TM(long long tm_work = 0, tm_rounds = 0;)
+        for (int r = -1;; r++) {
+            C2TM(const long long tm0 = c2_clock();)
+            if (work) {
+                // words [rd, wr) are unread (rd as C1 published it last round: never ahead of the truth).  Per round at most two
+                // chunks of S (a move draws 5 words on average, 11 at most), one of M (always 4) and one of R (3 per rotation).
+                // Every chunk finished here was issued a round ago or earlier; its successor is issued right away.
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                int roomS = (CREW_RING - (gS.wr - cs->rd[STREAM_S])) >> 2;
+#pragma unroll 1
+                for (int i = 0; i < 2 && roomS > 0; i++, roomS--) {
+                    c2_chunk_finish(gS, cs->pre[qS]);
+                    c2_chunk_issue(gS.mt, iS, cs->pre[qS]);
+                    qS ^= 1;
+                }
+                if (CREW_RING - (gM.wr - cs->rd[STREAM_M]) >= 4) { c2_chunk_finish(gM, cs->pre[2]); c2_chunk_issue(gM.mt, iM, cs->pre[2]); }
+                if (CREW_RING - (gR.wr - cs->rd[STREAM_R]) >= 4) { c2_chunk_finish(gR, cs->pre[3]); c2_chunk_issue(gR.mt, iR, cs->pre[3]); }
+                __threadfence_block();                      // ring words before the cursors that announce them
+                cs->wr[STREAM_M] = gM.wr; cs->wr[STREAM_S] = gS.wr; cs->wr[STREAM_R] = gR.wr;
+            }
+            C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
+            crew_bar(NT);
+            if (TL::alive(smem, r + 1) == 0) break;
+        }
+        if (work) asm volatile("cp.async.wait_all;" ::: "memory");       // (the copies in flight are simply dropped: nothing was consumed from them)
+        C2TM(if (blockIdx.x == 3 && lane == 0) printf("C3: rounds %lld work %lld\n", tm_rounds, tm_work / tm_rounds);)
+        // park the streams: unread ring words go back to the cursors (C1 published its final read positions)
+        if (mine) {
+            auto park = [&](const C2Gen &g, int s) {
+                MtCursor cur;
+                cur.par = g.par; cur.gen = g.gen; cur.fed = g.fed;
+                if (work) mt_cursor_rewind(cur, g.wr - cs->rd[s]);
+                cs->ctrl.rng[s] = cur;
+            };
+            park(gM, STREAM_M); park(gS, STREAM_S); park(gR, STREAM_R);
+        }
+    } else if (warp == 0) {
         // ================================================================ control warp C1: lane c <-> chain c
         // S stream, bookkeeping, modes.  Iteration r runs while the teams execute round r: it settles what they did in round
         // r - 1, adopts the move of round r, and writes its part of plan[(r + 1) & 1].
         const bool mine = lane < nloc;
-        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, stride, sys.n_mol);
+        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, sys.n_mol);
         C2Chain *cs = v.cs;
         ChainCtrl *c = &cs->ctrl;
         const tr_schedule &sch = cs->sch;
@@ -555,9 +683,9 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
         bool live = mine && !c->done;
         bool hot = false;
         int mode_prev = PLAN_IDLE, mode_cur = PLAN_IDLE;
-        bool total_for_init = false, filled = false;
+        bool total_for_init = false;
+        int starved = 0;                                         // consecutive rounds without the random words for the next move
         int commit_pending = 0;
-        int refill_cur = 3;
         int cur_info = 0, prev_info = 0;                         // m | sm << 16 | rot << 21 | magwalk << 22 | (axis + 1) << 23
         bool metro_ok = false;
         double rnd = 0.0, thr = 0.0, grd = 0.0;
@@ -644,25 +772,17 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
                 if (nR < 0) c->done = CHAIN_ABORT_RNG; else rdR += nR;
             }
         };
-        auto choose_refill = [&]() {
-            int aM = wrM - rdM, aS = wrS - rdS, aR = wrR - rdR;
-            if (refill_cur == STREAM_M) aM = CREW_RING;
-            if (refill_cur == STREAM_S) aS = CREW_RING;
-            if (refill_cur == STREAM_R) aR = CREW_RING;
-            int s = STREAM_M, amin = aM;
-            if (aS < amin) { amin = aS; s = STREAM_S; }
-            if (aR < amin) { amin = aR; s = STREAM_R; }
-            return amin <= CREW_RING_LOW ? s : 3;
-        };
         if (live) load_hot();
-        C2TM(long long tm_work = 0, tm_wait = 0, tm_rounds = 0;)
+        C2TM(long long tm_work = 0, tm_rounds = 0;)
+        crew_bar(NT);                                       // "rings filled"
+        C2TM(const long long tm_begin = c2_clock();)
 
         for (int r = -1;; r++) {
-            C2TM(const long long tm0 = clock64();)
+            C2TM(const long long tm0 = c2_clock();)
             C2Plan *pl = &cs->plan[(r + 1) & 1];
             const C2Plan *plc = &cs->plan[r & 1];
             int mode = PLAN_IDLE;
-            bool bubble = false;                                  // chain state changed under C2's eyes: post nothing this round
+            bool bubble = false;                                  // nothing is posted for this chain this round, but it is not finished
             if (live) {
                 wrM = cs->wr[STREAM_M]; wrS = cs->wr[STREAM_S]; wrR = cs->wr[STREAM_R];
                 // ---------------------------------------------- settle round r - 1
@@ -720,13 +840,13 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
                         crew_finish_point(P, c, sch, chain, etot, true);
                     }
                     load_hot();
-                    bubble = true;
+                    bubble = true;                                 // t / maxRot changed under C2's eyes: post the next move a round later
                 }
                 if (mode_cur == PLAN_MOVE) adopt(cA, plc);
                 metro_ok = false;
 
                 // ---------------------------------------------- plan round r + 1
-                int flags = 0, refill = 3, snap_slot = -1, movie_slot = -1;
+                int flags = 0, snap_slot = -1, movie_slot = -1;
                 if (mode_cur == PLAN_AUTO || mode_cur == PLAN_MOVE) {
                     // a move is being evaluated now; its Metropolis double sits at rdS (C2 forms the threshold from it) and both
                     // possible successors are drawn here; if all of that exists, the team may go on by itself
@@ -743,13 +863,11 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
                         pl->endS0 = cA.end; pl->endS1 = cB.end;
                         adopt_magw_rot = magw_rot; adopt_magw_trans = magw_trans;
                         flags = (t == 0.0) ? PF_TZERO : 0;
-                        refill = choose_refill();
                         budget--;
                     }
                     prev_info = cur_info;
                 } else if (mode_cur == PLAN_IDLE && !bubble) {
                     // nothing is running: everything that is not "next move of the same point" is decided here
-                    bool fill = false;
                     if (!c->done && !c->started) {
                         mode = PLAN_TOTAL; total_for_init = true;
                         snap_slot = (P.snap_sites && c->n_snaps < P.max_snaps) ? c->n_snaps : -1;
@@ -769,47 +887,39 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
                             write_cand(cA, &pl->cand[0]);
                             pl->endS0 = cA.end; pl->endS1 = cA.end;
                             adopt_magw_rot = magw_rot; adopt_magw_trans = magw_trans;
-                            mode = PLAN_MOVE; budget--; filled = false;
-                        } else if (!filled) { fill = true; filled = true; }     // the rings ran low: one blocking fill, then retry
+                            mode = PLAN_MOVE; budget--; starved = 0;
+                        } else if (++starved < C2_MAX_BUBBLES) bubble = true;      // C3 is still refilling: try again next round
                         else c->done = CHAIN_ABORT_RNG;
                     }
-                    if (fill || (mode == PLAN_IDLE && commit_pending)) mode = PLAN_SYNC;   // (parked with an accepted move not yet committed)
+                    if (mode == PLAN_IDLE && commit_pending) mode = PLAN_SYNC;   // (parked with an accepted move not yet committed)
                     if (mode != PLAN_IDLE) {
-                        flags = (commit_pending ? PF_COMMIT : 0) | (fill ? PF_FILL : 0);
+                        flags = commit_pending ? PF_COMMIT : 0;
                         commit_pending = 0;
-                        refill = fill ? 3 : choose_refill();
-                        if (fill) { cs->rd[STREAM_M] = rdM; cs->rd[STREAM_S] = rdS; cs->rd[STREAM_R] = rdR; }
                     }
                     if (c->done && mode == PLAN_IDLE && !bubble) live = false;
                 }
                 // (PLAN_TOTAL / PLAN_SYNC running now, or a bubble: wait)
-                pl->mode = mode; pl->flags = flags; pl->refill = refill; pl->snap_slot = snap_slot; pl->movie_slot = movie_slot;
+                pl->mode = mode; pl->flags = flags; pl->snap_slot = snap_slot; pl->movie_slot = movie_slot;
                 pl->kBt = kBt;
-                refill_cur = refill;
+                cs->rd[STREAM_M] = rdM; cs->rd[STREAM_S] = rdS; cs->rd[STREAM_R] = rdR;      // for C3: everything before these is consumed
             } else if (mine) pl->mode = PLAN_IDLE;
             const unsigned any = __ballot_sync(0xffffffffu, mode != PLAN_IDLE || mode_cur != PLAN_IDLE || (live && bubble));
             mode_prev = mode_cur; mode_cur = mode;
             if (lane == 0) TL::alive(smem, r + 1) = (int)any;
-            C2TM(const long long tm1 = clock64(); tm_work += tm1 - tm0; tm_rounds++;)
+            C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
             crew_bar(NT);
-            C2TM(tm_wait += clock64() - tm1;)
             if (!any) break;
         }
-        C2TM(if (blockIdx.x == 3 && lane == 0) printf("C1: rounds %lld work %lld wait %lld\n", tm_rounds, tm_work / tm_rounds, tm_wait / tm_rounds);)
-        // park the chain: counters into c, unread ring words back to the stream cursors
-        if (mine) {
-            if (hot) flush_hot();
-            mt_cursor_rewind(c->rng[STREAM_M], cs->wr[STREAM_M] - rdM);
-            mt_cursor_rewind(c->rng[STREAM_S], cs->wr[STREAM_S] - rdS);
-            mt_cursor_rewind(c->rng[STREAM_R], cs->wr[STREAM_R] - rdR);
-        }
+        C2TM(if (blockIdx.x == 3 && lane == 0) printf("C1: rounds %lld work %lld total/round %lld\n", tm_rounds, tm_work / tm_rounds, (c2_clock() - tm_begin) / tm_rounds);)
+        // park the chain: counters into c (C3 hands the unread ring words back to the stream cursors)
+        if (mine && hot) flush_hot();
     } else if (warp == 1) {
         // ================================================================ control warp C2: lane c <-> chain c
         // Everything transcendental.  Iteration r: (a) which move is in flight in round r follows from the plan C1 posted
         // for it and from the sign of the dE of round r - 1; (b) its Metropolis double and the threshold -kT log(rnd) on dE;
         // (c) the rotation draw of the NEXT move (Molecule.java:67-68) with sincos.  Both go into plan[(r + 1) & 1].
         const bool mine = lane < nloc;
-        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, stride, sys.n_mol);
+        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, sys.n_mol);
         C2Chain *cs = v.cs;
         const ChainCtrl *c = &cs->ctrl;
         const FastMod three = fastmod_make(3);
@@ -817,9 +927,10 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
         auto ringM = [&](int pos) { return cs->ring[STREAM_M][pos & (CREW_RING - 1)]; };
         auto ringS = [&](int pos) { return cs->ring[STREAM_S][pos & (CREW_RING - 1)]; };
         auto ringR = [&](int pos) { return cs->ring[STREAM_R][pos & (CREW_RING - 1)]; };
-        C2TM(long long tm_work = 0, tm_wait = 0, tm_rounds = 0;)
+        C2TM(long long tm_work = 0, tm_rounds = 0;)
+        crew_bar(NT);                                       // "rings filled"
         for (int r = -1;; r++) {
-            C2TM(const long long tm0 = clock64();)
+            C2TM(const long long tm0 = c2_clock();)
             if (mine) {
                 C2Plan *pl = &cs->plan[(r + 1) & 1];
                 const C2Plan *plc = &cs->plan[r & 1];
@@ -869,85 +980,111 @@ crew2_kernel(const __grid_constant__ KParams P, const int C, const int stride)
                 nR_next = nR;
                 pl->rnd = rnd; pl->thr = thr; pl->grd = grd; pl->sn = sn; pl->cs = csn; pl->axis = axis; pl->nR = nR;
             }
-            C2TM(const long long tm1 = clock64(); tm_work += tm1 - tm0; tm_rounds++;)
+            C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
             crew_bar(NT);
-            C2TM(tm_wait += clock64() - tm1;)
             if (TL::alive(smem, r + 1) == 0) break;
         }
-        C2TM(if (blockIdx.x == 3 && lane == 0) printf("C2: rounds %lld work %lld wait %lld\n", tm_rounds, tm_work / tm_rounds, tm_wait / tm_rounds);)
+        C2TM(if (blockIdx.x == 3 && lane == 0) printf("C2: rounds %lld work %lld\n", tm_rounds, tm_work / tm_rounds);)
     } else {
         // ================================================================ energy warps: one team <-> one chain
-        const int c = (warp - 2) * TPW + team;
+        const int c = (warp - C2_CTRL_WARPS) * TPW + team;
         const bool has = c < nloc;
-        const C2View v = c2_view<L, M, SS>(chains, has ? c : 0, stride, sys.n_mol);
+        const C2View v = c2_view<L, M, SS>(chains, has ? c : 0, C, sys.n_mol);
         C2Chain *cs = v.cs;
         unsigned ljb = 0;                                   // site slots b that hold a Lennard-Jones site in ANY particle (block-uniform)
         for (int p = 0; p < TL::NPOS; p++)
             if (info_valid(TL::pos_info(smem, p)) && info_lj(TL::pos_info(smem, p))) ljb |= 1u << ((p / L) % SS);
-        C2Pending<M> pend;
+        C2Pending pend;
         pend.tx = pend.ty = pend.tz = pend.cx = pend.cy = pend.cz = 0.0;
-        pend.pp = -1; pend.pm = -1;
-#pragma unroll
-        for (int k = 0; k < M; k++) { pend.e[k] = 0.0; pend.cidx[k] = -1; }
+        pend.pp = -1; pend.pm = -1; pend.m = -1;
         double last_dE = 0.0;
         int last_oob = 0;
+        crew_bar(NT);                                       // "rings filled"
         crew_bar(NT);                                       // plan[0] is written
-        C2TM(long long tm_work = 0, tm_wait = 0, tm_rounds = 0, tm_a = 0, tm_b = 0;)
+        C2TM(long long tm_work = 0, tm_rounds = 0, tm_a = 0, tm_b = 0;)
         for (int r = 0;; r++) {
             if (TL::alive(smem, r) == 0) break;
-            C2TM(const long long tm0 = clock64();)
-            if (has) {
-                const C2Plan *pl = &cs->plan[r & 1];
-                const int mode = pl->mode;
-                if (mode != PLAN_IDLE) {
-                    const int flags = pl->flags;
-                    const CrewWindow<L> w = c2_ring_begin<L>(cs, pl->refill, tl);    // loads fly while the move is evaluated
-                    int commit = flags & PF_COMMIT, which = 0;
-                    if (mode == PLAN_AUTO) {
-                        int acc, drew;
-                        crew_metropolis(last_oob, last_dE, (flags & PF_TZERO) != 0, true, pl->rnd, pl->thr, pl->grd, pl->kBt, acc, drew);
-                        commit = acc; which = drew;
+            C2TM(const long long tm0 = c2_clock();)
+            const C2Plan *pl = &cs->plan[r & 1];
+            const int mode = has ? pl->mode : PLAN_IDLE;
+            const bool moving = mode == PLAN_AUTO || mode == PLAN_MOVE;
+            int m = -1, sm = 0, lj = 0;
+            bool oob = false;
+            if (mode != PLAN_IDLE) {
+                const int flags = pl->flags;
+                int commit = flags & PF_COMMIT, which = 0;
+                if (mode == PLAN_AUTO) {
+                    int acc, drew;
+                    crew_metropolis(last_oob, last_dE, (flags & PF_TZERO) != 0, true, pl->rnd, pl->thr, pl->grd, pl->kBt, acc, drew);
+                    commit = acc; which = drew;
+                }
+                if (commit) {
+                    // setTemps (Molecule.java:128-135) of the move staged last, and its energies into the pair cache
+                    if (pend.pp >= 0) { v.xs[pend.pp] = pend.tx; v.ys[pend.pp] = pend.ty; v.zs[pend.pp] = pend.tz; }
+                    if (tl == 0 && pend.pm >= 0) { v.com[3 * pend.pm] = pend.cx; v.com[3 * pend.pm + 1] = pend.cy; v.com[3 * pend.pm + 2] = pend.cz; }
+#pragma unroll 1
+                    for (int k = 0; k < M; k++) {
+                        const int n = tl + L * k, pmv = pend.m;
+                        if ((n != pmv) & (n < sys.n_mol)) v.cache[tri_index(n < pmv ? n : pmv, n < pmv ? pmv : n)] = v.pend[k * L + tl];
                     }
-                    if (commit) {
-                        // setTemps (Molecule.java:128-135) of the move staged last, and its energies into the pair cache
-                        if (pend.pp >= 0) { v.xs[pend.pp] = pend.tx; v.ys[pend.pp] = pend.ty; v.zs[pend.pp] = pend.tz; }
-                        if (tl == 0 && pend.pm >= 0) { v.com[3 * pend.pm] = pend.cx; v.com[3 * pend.pm + 1] = pend.cy; v.com[3 * pend.pm + 2] = pend.cz; }
-#pragma unroll
-                        for (int k = 0; k < M; k++)
-                            if (pend.cidx[k] >= 0) v.cache[pend.cidx[k]] = pend.e[k];
+                }
+                __syncwarp(mask);
+                if (moving) {
+                    const C2Cand d = pl->cand[which];
+                    m = d.m; sm = d.info & 0xff;
+                    oob = c2_geometry<L, M, SS>(smem, v, sys, d, pl, tl, pend, lj);
+                    // a team with fewer staged sites than another team of the warp: neutral entries up to the common bound
+                    if (tl >= sm && tl < SS) {
+                        C2Stage st;
+                        st.nx = st.ny = st.nz = -FAR_AWAY;       // (not +FAR_AWAY: empty site slots sit there, and r = 0 would give NaN)
+                        st.kq = 0.0; st.row = 0; st.lj = 0; st.pad_[0] = st.pad_[1] = 0;
+                        v.stage[tl] = st;
                     }
-                    __syncwarp(mask);
-                    C2TM(const long long tma = clock64(); tm_a += tma - tm0;)
-                    if (mode == PLAN_AUTO || mode == PLAN_MOVE) {
-                        const C2Cand d = pl->cand[which];
-                        c2_move<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, d, pl, ljb, tl, mask, &cs->result[r & 1], pend, last_dE, last_oob);
-                    } else if (mode == PLAN_TOTAL) {
-                        const double e = c2_total_energy<L, M, SS, HAS_EXP>(smem, v, sys, tl, mask);
-                        if (tl == 0) cs->etot = e;
-                        const int k = pl->snap_slot, mv = pl->movie_slot;
-                        if (k >= 0)
-                            c2_sites_to_global<L, M, SS>(v, P.snap_sites + ((size_t)(chain0 + c) * P.max_snaps + k) * (size_t)sys.n_sites * 3, sys, tl);
-                        if (mv >= 0)
-                            c2_sites_to_global<L, M, SS>(v, P.movie_sites + ((size_t)(chain0 + c) * P.max_points + mv) * (size_t)sys.n_sites * 3, sys, tl);
-                    }
-                    C2TM(const long long tmb = clock64(); tm_b += tmb - tma;)
-                    c2_ring_end<L>(cs, w, tl, mask);
-                    if (flags & PF_FILL) c2_ring_fill<L>(cs, tl, mask);
+                } else if (mode == PLAN_TOTAL) {
+                    c2_total_round<L, M, SS, HAS_EXP>(smem, v, P, chain0 + c, pl->snap_slot, pl->movie_slot, tl, mask);
                 }
             }
-            C2TM(const long long tm1 = clock64(); tm_work += tm1 - tm0; tm_rounds++;)
+            C2TM(const long long tma = c2_clock(); tm_a += tma - tm0;)
+            // warp-wide: who is out of bounds (per team), the most staged sites of any team, which staged sites are Lennard-Jones
+            const unsigned oob_w = __ballot_sync(0xffffffffu, oob);
+            const unsigned lj_w = __ballot_sync(0xffffffffu, lj != 0);
+            __syncwarp();                                   // staging stores before the reads below
+            const bool team_oob = (oob_w & mask) != 0u;
+            const bool eval = moving && !team_oob;
+            const int sm_w = __reduce_max_sync(0xffffffffu, eval ? sm : 0);
+            unsigned ljw = 0;                               // bit a: staged site a is a Lennard-Jones site in some team
+#pragma unroll
+            for (int t4 = 0; t4 < TPW; t4++) ljw |= (lj_w >> (t4 * L)) & ((1u << SS) - 1u);
+            if (sm_w > 0) {
+                double dl = 0.0, sl = 0.0, el = 0.0;
+                if (eval) c2_evaluate<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, m, sm_w, ljw, ljb, tl, dl, sl, el);
+                const double dE = crew_team_sum<L>(dl, mask);
+                if (TRACE) { sl = crew_team_sum<L>(sl, mask); el = crew_team_sum<L>(el, mask); }
+                if (eval) {
+                    if (tl == 0) {
+                        CrewResult *res = &cs->result[r & 1];
+                        res->oob = 0; res->dE = dE;
+                        if (TRACE) { res->eS = sl; res->eE = el; }
+                    }
+                    last_dE = dE; last_oob = 0;
+                }
+            }
+            if (moving && team_oob) {
+                if (tl == 0) cs->result[r & 1].oob = 1;
+                last_dE = 0.0; last_oob = 1;
+            }
+            C2TM(tm_b += c2_clock() - tma; tm_work += c2_clock() - tm0; tm_rounds++;)
             crew_bar(NT);
-            C2TM(tm_wait += clock64() - tm1;)
         }
-        C2TM(if (blockIdx.x == 3 && lane == 0) printf("E%d: rounds %lld work %lld (plan+commit %lld, move %lld) wait %lld\n", warp, tm_rounds, tm_work / tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds, tm_wait / tm_rounds);)
+        C2TM(if (blockIdx.x == 3 && lane == 0) printf("E%d: rounds %lld work %lld (plan+commit+geometry %lld, evaluate %lld)\n", warp, tm_rounds, tm_work / tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds);)
     }
     __syncthreads();
 
     // chain state -> global memory
-    for (int c0 = warp * TPW; c0 < nloc; c0 += (2 + EW) * TPW) {
+    for (int c0 = warp * TPW; c0 < nloc; c0 += NW * TPW) {
         const int c = c0 + team;
         if (c >= nloc) continue;
-        const C2View v = c2_view<L, M, SS>(chains, c, stride, sys.n_mol);
+        const C2View v = c2_view<L, M, SS>(chains, c, C, sys.n_mol);
         const long long ch = chain0 + c;
         int *dst = (int *)(P.ctrl + ch);
         const int *src = (const int *)&v.cs->ctrl;

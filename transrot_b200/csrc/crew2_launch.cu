@@ -11,13 +11,21 @@ using namespace tr;
 namespace {
 
 #ifndef TR_CREW2_EW
-#define TR_CREW2_EW 7          // energy warps per block (+ 2 control warps)
+#define TR_CREW2_EW 7          // energy warps per block (+ 3 control warps)
 #endif
 
 // Instantiated (L lanes per team, M particle slots per lane, SS site slots per particle); capacity L * M particles of up to
 // SS sites.  Order = preference: 8-lane teams (four chains per energy warp) while the particles fit.
 const Crew2Variant kCrew2[] = { {8, 1, 1}, {8, 1, 3}, {8, 1, 5}, {8, 2, 3}, {8, 3, 3}, {8, 2, 5}, {8, 4, 3}, {8, 3, 5}, {8, 4, 5} };
 
+#ifdef TR_CREW2_DEV      // development builds (tools/devbuild.sh): the two variants of the shipped sample and of (H2O)20 only
+#define TR_CREW2_CASES(CALL)                                                       \
+    switch (v.L * 10000 + v.M * 100 + v.SS) {                                      \
+    case 80105: CALL(8, 1, 5); break;                                              \
+    case 80303: CALL(8, 3, 3); break;                                              \
+    default: return fail(ctx, TR_ELIMIT, "Error: no crew2 kernel for %d lanes x %d particles x %d sites (development build)", v.L, v.M, v.SS); \
+    }
+#else
 #define TR_CREW2_CASES(CALL)                                                       \
     switch (v.L * 10000 + v.M * 100 + v.SS) {                                      \
     case 80101: CALL(8, 1, 1); break;                                              \
@@ -31,12 +39,13 @@ const Crew2Variant kCrew2[] = { {8, 1, 1}, {8, 1, 3}, {8, 1, 5}, {8, 2, 3}, {8, 
     case 80405: CALL(8, 4, 5); break;                                              \
     default: return fail(ctx, TR_ELIMIT, "Error: no crew2 kernel for %d lanes x %d particles x %d sites", v.L, v.M, v.SS); \
     }
+#endif
 
 template <int L, int M, int SS>
 void sizes_t(const tr_ctx *ctx, int *tables, int *stride, int *tri)
 {
     *tables = C2Tables<L, M, SS>::table_bytes(ctx->sys.n_types, ctx->sys.has_exp != 0);
-    *stride = C2Tables<L, M, SS>::chain_bytes(ctx->sys.n_mol);
+    *stride = C2Tables<L, M, SS>::ctrl_bytes() + C2Tables<L, M, SS>::team_bytes(ctx->sys.n_mol);
     *tri = C2Tables<L, M, SS>::tri_count(ctx->sys.n_mol);
 }
 
@@ -59,7 +68,7 @@ int geometry(tr_ctx *ctx, int *C, int *stride, int *smem, int *tri)
 }
 
 template <int L, int M, int SS>
-cudaError_t launch_t(tr_ctx *ctx, const KParams &P, int C, int stride, int smem)
+cudaError_t launch_t(tr_ctx *ctx, const KParams &P, int C, int smem)
 {
     constexpr int EW = TR_CREW2_EW;
     const unsigned blocks = (unsigned)((P.n_chains + C - 1) / C);
@@ -68,7 +77,7 @@ cudaError_t launch_t(tr_ctx *ctx, const KParams &P, int C, int stride, int smem)
     {                                                                                                                      \
         auto kern = crew2_kernel<L, M, SS, HE, TRC, EW>;                                                                   \
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e; \
-        kern<<<blocks, 32 * (2 + EW), smem, ctx->stream>>>(P, C, stride);                                                  \
+        kern<<<blocks, 32 * (C2_CTRL_WARPS + EW), smem, ctx->stream>>>(P, C);                                              \
     }
     if (P.sys.has_exp) { if (P.trace) TR_C2_LAUNCH(true, true) else TR_C2_LAUNCH(true, false) }
     else { if (P.trace) TR_C2_LAUNCH(false, true) else TR_C2_LAUNCH(false, false) }
@@ -100,7 +109,7 @@ int launch_crew2(tr_ctx *ctx, const KParams &P)
     if (int r = geometry(ctx, &C, &stride, &smem, &tri)) return r;
     const Crew2Variant v = ctx->crew2;
     cudaError_t e = cudaErrorInvalidValue;
-#define CALL_LAUNCH(L, M, SS) e = launch_t<L, M, SS>(ctx, P, C, stride, smem)
+#define CALL_LAUNCH(L, M, SS) e = launch_t<L, M, SS>(ctx, P, C, smem)
     TR_CREW2_CASES(CALL_LAUNCH)
 #undef CALL_LAUNCH
     if (e != cudaSuccess) return fail(ctx, TR_ECUDA, "Error: crew2 kernel launch failed: %s", cudaGetErrorString(e));
