@@ -101,17 +101,22 @@ struct C2Tables {
     static constexpr int OFF_CD = OFF_QPOS + NPOS * 8;
 
     __host__ __device__ static int table_bytes(int n_types, bool has_exp) { return (OFF_CD + n_types * (n_types + 1) * 16 * (has_exp ? 2 : 1) + 127) & ~127; }
-    __host__ __device__ static int tri_count(int n_mol) { return (n_mol * (n_mol - 1) / 2 + 1) & ~1; }
+    __host__ __device__ static int tri_count(int n_mol) { return (n_mol * (n_mol - 1) / 2 + 1) & ~1; }     // global copy (KParams::pair_cache)
+    // team region, every offset a compile-time constant (sized for the NMOL particle slots, whatever n_mol is): one base
+    // register per chain serves every access
+    static constexpr int T_STAGE = 0;
+    static constexpr int T_COM = T_STAGE + SS * (int)sizeof(C2Stage);
+    static constexpr int T_XS = T_COM + align16(NMOL * 24);
+    static constexpr int T_YS = T_XS + NPOS * 8;
+    static constexpr int T_ZS = T_YS + NPOS * 8;
+    static constexpr int T_PEND = T_ZS + NPOS * 8;
+    static constexpr int T_CACHE = T_PEND + NMOL * 8;
+    static constexpr int T_END = T_CACHE + ((NMOL * (NMOL - 1) / 2 + 1) & ~1) * 8;
     // control region: 16 mod 128 bytes, so that the lanes of a control warp (one chain each) spread over the banks
     __host__ __device__ static constexpr int ctrl_bytes() { return ((align16((int)sizeof(C2Chain)) + 127) & ~127) + 16; }
     // team region: 64 mod 128 bytes, so that the two teams a 64-bit access serves in one pass (8 lanes x 8 bytes each) fall
     // into different banks
-    __host__ __device__ static int team_bytes(int n_mol)
-    {
-        int b = SS * (int)sizeof(C2Stage) + align16(n_mol * 24) + NPOS * 24 + NMOL * 8 + tri_count(n_mol) * 8;
-        b = (b + 127) & ~127;
-        return b + 64;
-    }
+    __host__ __device__ static constexpr int team_bytes() { return ((T_END + 127) & ~127) + 64; }
 
     __device__ static __forceinline__ int &alive(unsigned char *smem, int round) { return ((int *)smem)[round & 1]; }
     __device__ static __forceinline__ int mol_ns(const unsigned char *smem, int m) { return *(const int *)(smem + OFF_MOL_NS + 4 * m); }
@@ -160,15 +165,14 @@ __device__ __forceinline__ C2View c2_view(unsigned char *chains, int c, int C, i
     using TL = C2Tables<L, M, SS>;
     constexpr int NPOS = L * M * SS;
     C2View v;
-    v.cs = (C2Chain *)(chains + (size_t)c * TL::ctrl_bytes());
-    unsigned char *b = chains + (size_t)C * TL::ctrl_bytes() + (size_t)c * TL::team_bytes(n_mol);
-    v.stage = (C2Stage *)b;
-    b += SS * (int)sizeof(C2Stage);
-    v.com = (double *)b;
-    b += align16(n_mol * 24);
-    v.xs = (double *)b; v.ys = v.xs + NPOS; v.zs = v.ys + NPOS;
-    v.pend = v.zs + NPOS;                          // [M][L]: per-neighbour energies of the move staged last
-    v.cache = v.pend + L * M;
+    v.cs = (C2Chain *)(chains + c * TL::ctrl_bytes());
+    unsigned char *b = chains + C * TL::ctrl_bytes() + c * TL::team_bytes();
+    v.stage = (C2Stage *)(b + TL::T_STAGE);
+    v.com = (double *)(b + TL::T_COM);
+    v.xs = (double *)(b + TL::T_XS); v.ys = (double *)(b + TL::T_YS); v.zs = (double *)(b + TL::T_ZS);
+    v.pend = (double *)(b + TL::T_PEND);           // [M][L]: per-neighbour energies of the move staged last
+    v.cache = (double *)(b + TL::T_CACHE);
+    (void)n_mol; (void)NPOS;
     return v;
 }
 
@@ -445,6 +449,93 @@ __device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2V
     }
 }
 
+// The same for small lanes (M * SS site slots <= C2_WIDE_MAX): ALL of this lane's site slots against one staged site at a time
+// - M * SS independent evaluations in flight, which hides the FP64 latency from a single warp - in a real loop over the staged
+// sites.  Also folds in the pair-cache update of the move committed at the top of this round (`commit_prev`, particle
+// `m_prev`): entry (m_prev, n) is written before entry (m, n) is read, by the lane that owns n.
+constexpr int C2_WIDE_MAX = 10;
+
+template <int L, int M, int SS, bool HAS_EXP, bool TRACE>
+__device__ __forceinline__ void c2_evaluate_wide(const unsigned char *smem, const C2View &v, const DevSystem &sys, int m, int sm_w, unsigned ljw,
+                                                 unsigned ljb, int tl, const double (&x)[M * SS], const double (&y)[M * SS], const double (&z)[M * SS],
+                                                 const double (&q)[M * SS], double &dl, double &sl, double &el)
+{
+    using TL = C2Tables<L, M, SS>;
+    constexpr int NE = M * SS;
+    const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
+    const int nmol = sys.n_mol;
+    // the cached energies this move is measured against (the commit of the previous move is in the cache: the team synchronised)
+    double e[M], eold[M];
+    bool on[M];
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        const int n = tl + L * k;
+        on[k] = (n != m) & (n < nmol);
+        const int lo = n < m ? n : m, hi = n < m ? m : n;
+        eold[k] = v.cache[on[k] ? tri_index(lo, hi) : 0];
+        e[k] = 0.0;
+    }
+#pragma unroll 1
+    for (int a = 0; a < sm_w; a++) {
+        const C2Stage st = v.stage[a];
+        double r2[NE], y0[NE], t[NE], u[NE], p[NE], ri[NE];
+#pragma unroll
+        for (int j = 0; j < NE; j++) { const double d = x[j] - st.nx; r2[j] = d * d; }
+#pragma unroll
+        for (int j = 0; j < NE; j++) { const double d = y[j] - st.ny; r2[j] = fma(d, d, r2[j]); }
+#pragma unroll
+        for (int j = 0; j < NE; j++) { const double d = z[j] - st.nz; r2[j] = fma(d, d, r2[j]); }
+#pragma unroll
+        for (int j = 0; j < NE; j++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[j]) : "d"(r2[j]));
+#pragma unroll
+        for (int j = 0; j < NE; j++) t[j] = r2[j] * y0[j];
+#pragma unroll
+        for (int j = 0; j < NE; j++) u[j] = fma(-t[j], y0[j], 1.0);
+#pragma unroll
+        for (int j = 0; j < NE; j++) p[j] = fma(u[j], 0.375, 0.5);
+#pragma unroll
+        for (int j = 0; j < NE; j++) u[j] = y0[j] * u[j];
+#pragma unroll
+        for (int j = 0; j < NE; j++) ri[j] = fma(p[j], u[j], y0[j]);
+#pragma unroll
+        for (int j = 0; j < NE; j++) e[j / SS] = fma(st.kq * q[j], ri[j], e[j / SS]);
+        if (HAS_EXP || ((ljw >> a) & 1u)) {
+#pragma unroll
+            for (int j = 0; j < NE; j++) {
+                if (HAS_EXP || ((ljb >> (j % SS)) & 1u)) {
+                    const int cj = info_col(TL::pos_info(smem, j * L + tl));
+                    const double2 cd = *(const double2 *)(tab_cd + st.row + cj);
+                    const double i2 = ri[j] * ri[j];
+                    const double i6 = i2 * i2 * i2;
+                    e[j / SS] = fma(fma(cd.y, i6, -cd.x), i6, e[j / SS]);                  // + D/r^12 - C/r^6
+                    if (HAS_EXP) {
+                        const double2 ab = *(const double2 *)(tab_ab + st.row + cj);
+                        e[j / SS] = fma(ab.x, exp(-ab.y * (r2[j] * ri[j])), e[j / SS]);
+                    }
+                }
+            }
+        }
+    }
+    dl = 0.0; sl = 0.0; el = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        v.pend[k * L + tl] = e[k];                            // waits for the commit
+        dl += on[k] ? e[k] - eold[k] : 0.0;                   // eEnd - eStart from per-neighbour differences
+        if (TRACE) { sl += on[k] ? eold[k] : 0.0; el += on[k] ? e[k] : 0.0; }
+    }
+}
+
+// The pair-cache half of a commit (the energies the accepted move left in C2View::pend), when no evaluation follows it.
+template <int L, int M>
+__device__ __noinline__ void c2_commit_cache(const C2View &v, int n_mol, int m_prev, int tl)
+{
+#pragma unroll 1
+    for (int k = 0; k < M; k++) {
+        const int n = tl + L * k;
+        if ((n != m_prev) & (n < n_mol)) v.cache[tri_index(n < m_prev ? n : m_prev, n < m_prev ? m_prev : n)] = v.pend[k * L + tl];
+    }
+}
+
 // Space.calcEnergy (Space.java:648-658) of the committed structure, one team; every particle-pair energy is stored into
 // the cache on the way (this = the lower-indexed particle, as Space.calcEnergy has it).
 template <int L, int M, int SS, bool HAS_EXP>
@@ -538,8 +629,11 @@ struct C2Pick {                      // the S-stream part of a move starting at 
 
 constexpr int C2_CTRL_WARPS = 3;
 
+#ifndef TR_CREW2_MINB
+#define TR_CREW2_MINB 1
+#endif
 template <int L, int M, int SS, bool HAS_EXP, bool TRACE, int EW>
-__global__ void __launch_bounds__(32 * (C2_CTRL_WARPS + EW), 1)
+__global__ void __launch_bounds__(32 * (C2_CTRL_WARPS + EW), TR_CREW2_MINB)
 crew2_kernel(const __grid_constant__ KParams P, const int C)
 {
     using TL = C2Tables<L, M, SS>;
@@ -1006,31 +1100,50 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             if (TL::alive(smem, r) == 0) break;
             C2TM(const long long tm0 = c2_clock();)
             const C2Plan *pl = &cs->plan[r & 1];
-            const int mode = has ? pl->mode : PLAN_IDLE;
+            const int4 hdr = *(const int4 *)&pl->mode;       // mode, flags, snap_slot, movie_slot
+            const int mode = has ? hdr.x : PLAN_IDLE;
             const bool moving = mode == PLAN_AUTO || mode == PLAN_MOVE;
-            int m = -1, sm = 0, lj = 0;
+            // Which successor was posted for "a Metropolis double was drawn for the move of last round" is known without the plan
+            // (Space.java:720: drawn iff dE > 0): its descriptor is fetched while the Metropolis test is still being decided.
+            const int which = (mode == PLAN_AUTO && !last_oob && last_dE > 0.0) ? 1 : 0;
+            const C2Cand d = pl->cand[which];
+            int m = -1, sm = 0, lj = 0, commit = 0;
+            const int m_prev = pend.m;
+            constexpr int WN = (M * SS <= C2_WIDE_MAX) ? M * SS : 1;
+            double wx[WN], wy[WN], wz[WN], wq[WN];
+#pragma unroll
+            for (int j = 0; j < WN; j++) wx[j] = wy[j] = wz[j] = wq[j] = 0.0;
             bool oob = false;
             if (mode != PLAN_IDLE) {
-                const int flags = pl->flags;
-                int commit = flags & PF_COMMIT, which = 0;
+                const int flags = hdr.y;
+                commit = flags & PF_COMMIT;
                 if (mode == PLAN_AUTO) {
                     int acc, drew;
                     crew_metropolis(last_oob, last_dE, (flags & PF_TZERO) != 0, true, pl->rnd, pl->thr, pl->grd, pl->kBt, acc, drew);
-                    commit = acc; which = drew;
+                    commit = acc;
                 }
                 if (commit) {
-                    // setTemps (Molecule.java:128-135) of the move staged last, and its energies into the pair cache
+                    // setTemps (Molecule.java:128-135) of the move staged last, and its per-neighbour energies into the pair cache
                     if (pend.pp >= 0) { v.xs[pend.pp] = pend.tx; v.ys[pend.pp] = pend.ty; v.zs[pend.pp] = pend.tz; }
                     if (tl == 0 && pend.pm >= 0) { v.com[3 * pend.pm] = pend.cx; v.com[3 * pend.pm + 1] = pend.cy; v.com[3 * pend.pm + 2] = pend.cz; }
-#pragma unroll 1
-                    for (int k = 0; k < M; k++) {
-                        const int n = tl + L * k, pmv = pend.m;
-                        if ((n != pmv) & (n < sys.n_mol)) v.cache[tri_index(n < pmv ? n : pmv, n < pmv ? pmv : n)] = v.pend[k * L + tl];
-                    }
+                    if constexpr (M * SS <= C2_WIDE_MAX) {
+#pragma unroll
+                        for (int k = 0; k < M; k++) {
+                            const int n = tl + L * k;
+                            if ((n != m_prev) & (n < sys.n_mol)) v.cache[tri_index(n < m_prev ? n : m_prev, n < m_prev ? m_prev : n)] = v.pend[k * L + tl];
+                        }
+                    } else c2_commit_cache<L, M>(v, sys.n_mol, m_prev, tl);
                 }
                 __syncwarp(mask);
                 if (moving) {
-                    const C2Cand d = pl->cand[which];
+                    // this lane's own coordinates and charges: the loads fly while the trial geometry is built (the slot of the moved
+                    // particle itself is discarded, so the rotateTemp round trip below does not matter here)
+                    if constexpr (M * SS <= C2_WIDE_MAX) {
+#pragma unroll
+                        for (int j = 0; j < WN; j++) {
+                            wx[j] = v.xs[j * L + tl]; wy[j] = v.ys[j * L + tl]; wz[j] = v.zs[j * L + tl]; wq[j] = TL::qpos(smem, j * L + tl);
+                        }
+                    }
                     m = d.m; sm = d.info & 0xff;
                     oob = c2_geometry<L, M, SS>(smem, v, sys, d, pl, tl, pend, lj);
                     // a team with fewer staged sites than another team of the warp: neutral entries up to the common bound
@@ -1040,9 +1153,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
                         st.kq = 0.0; st.row = 0; st.lj = 0; st.pad_[0] = st.pad_[1] = 0;
                         v.stage[tl] = st;
                     }
-                } else if (mode == PLAN_TOTAL) {
-                    c2_total_round<L, M, SS, HAS_EXP>(smem, v, P, chain0 + c, pl->snap_slot, pl->movie_slot, tl, mask);
-                }
+                } else if (mode == PLAN_TOTAL) c2_total_round<L, M, SS, HAS_EXP>(smem, v, P, chain0 + c, hdr.z, hdr.w, tl, mask);
             }
             C2TM(const long long tma = c2_clock(); tm_a += tma - tm0;)
             // warp-wide: who is out of bounds (per team), the most staged sites of any team, which staged sites are Lennard-Jones
@@ -1057,7 +1168,10 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             for (int t4 = 0; t4 < TPW; t4++) ljw |= (lj_w >> (t4 * L)) & ((1u << SS) - 1u);
             if (sm_w > 0) {
                 double dl = 0.0, sl = 0.0, el = 0.0;
-                if (eval) c2_evaluate<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, m, sm_w, ljw, ljb, tl, dl, sl, el);
+                if (eval) {
+                    if constexpr (M * SS <= C2_WIDE_MAX) c2_evaluate_wide<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, m, sm_w, ljw, ljb, tl, wx, wy, wz, wq, dl, sl, el);
+                    else c2_evaluate<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, m, sm_w, ljw, ljb, tl, dl, sl, el);
+                }
                 const double dE = crew_team_sum<L>(dl, mask);
                 if (TRACE) { sl = crew_team_sum<L>(sl, mask); el = crew_team_sum<L>(el, mask); }
                 if (eval) {

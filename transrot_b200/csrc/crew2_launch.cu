@@ -16,13 +16,18 @@ namespace {
 
 // Instantiated (L lanes per team, M particle slots per lane, SS site slots per particle); capacity L * M particles of up to
 // SS sites.  Order = preference: 8-lane teams (four chains per energy warp) while the particles fit.
-const Crew2Variant kCrew2[] = { {8, 1, 1}, {8, 1, 3}, {8, 1, 5}, {8, 2, 3}, {8, 3, 3}, {8, 2, 5}, {8, 4, 3}, {8, 3, 5}, {8, 4, 5} };
+const Crew2Variant kCrew2[] = {
+#ifdef TR_CREW2_L16
+    {16, 2, 3},
+#endif
+    {8, 1, 1}, {8, 1, 3}, {8, 1, 5}, {8, 2, 3}, {8, 3, 3}, {8, 2, 5}, {8, 4, 3}, {8, 3, 5}, {8, 4, 5} };
 
 #ifdef TR_CREW2_DEV      // development builds (tools/devbuild.sh): the two variants of the shipped sample and of (H2O)20 only
 #define TR_CREW2_CASES(CALL)                                                       \
     switch (v.L * 10000 + v.M * 100 + v.SS) {                                      \
     case 80105: CALL(8, 1, 5); break;                                              \
     case 80303: CALL(8, 3, 3); break;                                              \
+    case 160203: CALL(16, 2, 3); break;                                            \
     default: return fail(ctx, TR_ELIMIT, "Error: no crew2 kernel for %d lanes x %d particles x %d sites (development build)", v.L, v.M, v.SS); \
     }
 #else
@@ -45,7 +50,7 @@ template <int L, int M, int SS>
 void sizes_t(const tr_ctx *ctx, int *tables, int *stride, int *tri)
 {
     *tables = C2Tables<L, M, SS>::table_bytes(ctx->sys.n_types, ctx->sys.has_exp != 0);
-    *stride = C2Tables<L, M, SS>::ctrl_bytes() + C2Tables<L, M, SS>::team_bytes(ctx->sys.n_mol);
+    *stride = C2Tables<L, M, SS>::ctrl_bytes() + C2Tables<L, M, SS>::team_bytes();
     *tri = C2Tables<L, M, SS>::tri_count(ctx->sys.n_mol);
 }
 
@@ -56,7 +61,7 @@ int geometry(tr_ctx *ctx, int *C, int *stride, int *smem, int *tri)
 #define CALL_SIZES(L, M, SS) sizes_t<L, M, SS>(ctx, &tables, stride, tri)
     TR_CREW2_CASES(CALL_SIZES)
 #undef CALL_SIZES
-    int c = TR_CREW2_EW * (32 / v.L);                 // every chain of a block has its own energy team and control lane
+    int c = TR_CREW2_EW * 4;                          // every chain of a block has its own energy team and control lane
     if (ctx->crew_chains > 0) c = std::min(c, ctx->crew_chains);
     const int c_fit = (ctx->max_smem_optin - tables) / *stride;
     if (c_fit < 1)
@@ -70,7 +75,7 @@ int geometry(tr_ctx *ctx, int *C, int *stride, int *smem, int *tri)
 template <int L, int M, int SS>
 cudaError_t launch_t(tr_ctx *ctx, const KParams &P, int C, int smem)
 {
-    constexpr int EW = TR_CREW2_EW;
+    constexpr int EW = TR_CREW2_EW * (L / 8);        // 28 chains per block either way: four per energy warp (L = 8) or two (L = 16)
     const unsigned blocks = (unsigned)((P.n_chains + C - 1) / C);
     cudaError_t e;
 #define TR_C2_LAUNCH(HE, TRC)                                                                                              \
