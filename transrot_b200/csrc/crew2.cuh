@@ -41,6 +41,17 @@ __device__ __forceinline__ long long c2_clock() { long long t; asm volatile("mov
 #define C2TM(...)
 #endif
 
+// Round synchronisation.  The energy warps and the control warps meet through two pairs of named barriers instead of one
+// block-wide barrier per round, so that an energy warp never waits for ANOTHER ENERGY WARP: it starts round r + 1 as soon as
+// it has finished round r and the control warps have posted plan r + 1 (which they do during round r, from the results of
+// round r - 1).  The control warps start iteration i when every energy warp has posted its results of round i - 1.
+//   plan barrier p (ids 2, 3; parity of the round the plan is for): control warps ARRIVE after writing the plan, energy warps WAIT.
+//   result barrier p (ids 4, 5; parity of the round): energy warps ARRIVE after posting results, control warps WAIT.
+// Energy warps that share an SM sub-partition drift out of phase this way, and their FP64 bursts stop colliding.
+__device__ __forceinline__ void c2_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void c2_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+constexpr int C2_BAR_PLAN = 2, C2_BAR_RES = 4;
+
 constexpr int C2_RING_NEED_M = 4;      // M words a move consumes, always (Main.java:199-208)
 constexpr int C2_RING_NEED_R = 8;      // R words guaranteed before a move is posted: angle double + up to 6 nextInt(3) tries
 constexpr int C2_MAX_BUBBLES = 256;    // rounds a chain may wait for random words before it is abandoned (CHAIN_ABORT_RNG)
@@ -106,9 +117,8 @@ struct C2Tables {
     // register per chain serves every access
     static constexpr int T_STAGE = 0;
     static constexpr int T_COM = T_STAGE + SS * (int)sizeof(C2Stage);
-    static constexpr int T_XS = T_COM + align16(NMOL * 24);
-    static constexpr int T_YS = T_XS + NPOS * 8;
-    static constexpr int T_ZS = T_YS + NPOS * 8;
+    static constexpr int T_XY = T_COM + align16(NMOL * 24);     // [NPOS] double2 {x, y}: one 16-byte load per site slot
+    static constexpr int T_ZS = T_XY + NPOS * 16;               // [NPOS] double
     static constexpr int T_PEND = T_ZS + NPOS * 8;
     static constexpr int T_CACHE = T_PEND + NMOL * 8;
     static constexpr int T_END = T_CACHE + ((NMOL * (NMOL - 1) / 2 + 1) & ~1) * 8;
@@ -155,7 +165,8 @@ struct C2Tables {
 struct C2View {
     C2Chain *cs;
     C2Stage *stage;
-    double *com, *xs, *ys, *zs, *cache, *pend;
+    double2 *xy;
+    double *com, *zs, *cache, *pend;
 };
 
 // Block layout: tables | C control regions | C team regions
@@ -169,7 +180,7 @@ __device__ __forceinline__ C2View c2_view(unsigned char *chains, int c, int C, i
     unsigned char *b = chains + C * TL::ctrl_bytes() + c * TL::team_bytes();
     v.stage = (C2Stage *)(b + TL::T_STAGE);
     v.com = (double *)(b + TL::T_COM);
-    v.xs = (double *)(b + TL::T_XS); v.ys = (double *)(b + TL::T_YS); v.zs = (double *)(b + TL::T_ZS);
+    v.xy = (double2 *)(b + TL::T_XY); v.zs = (double *)(b + TL::T_ZS);
     v.pend = (double *)(b + TL::T_PEND);           // [M][L]: per-neighbour energies of the move staged last
     v.cache = (double *)(b + TL::T_CACHE);
     (void)n_mol; (void)NPOS;
@@ -352,7 +363,8 @@ __device__ __forceinline__ bool c2_geometry(const unsigned char *smem, const C2V
     if (tl < sm) {
         const int p = TL::pos_of(m, tl);
         const int inf = TL::pos_info(smem, p);
-        double ox = v.xs[p], oy = v.ys[p], oz = v.zs[p], tx, ty, tz;
+        const double2 oxy = v.xy[p];
+        double ox = oxy.x, oy = oxy.y, oz = v.zs[p], tx, ty, tz;
         if (rot) {
             // Molecule.java:70-95, operation for operation, no contraction
             const double cx = v.com[3 * m], cy = v.com[3 * m + 1], cz = v.com[3 * m + 2];
@@ -370,7 +382,7 @@ __device__ __forceinline__ bool c2_geometry(const unsigned char *smem, const C2V
             ty = axis == 0 ? ru : (axis == 1 ? ay : rw);
             tz = axis == 2 ? az : rw;
             // a.x += x: the committed coordinate keeps the (a.x - x) + x round trip even if the move is rejected
-            v.xs[p] = __dadd_rn(ax, cx); v.ys[p] = __dadd_rn(ay, cy); v.zs[p] = __dadd_rn(az, cz);
+            v.xy[p] = make_double2(__dadd_rn(ax, cx), __dadd_rn(ay, cy)); v.zs[p] = __dadd_rn(az, cz);
             tx = __dadd_rn(tx, cx); ty = __dadd_rn(ty, cy); tz = __dadd_rn(tz, cz);
         } else {
             tx = __dadd_rn(ox, d.va); ty = __dadd_rn(oy, d.vb); tz = __dadd_rn(oz, d.vc);
@@ -421,7 +433,8 @@ __device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2V
         } else { snx[a] = sny[a] = snz[a] = skq[a] = 0.0; srow[a] = 0; }
     }
     dl = 0.0; sl = 0.0; el = 0.0;
-    const double *px = v.xs + tl, *py = v.ys + tl, *pz = v.zs + tl;
+    const double2 *pxy = v.xy + tl;
+    const double *pz = v.zs + tl;
     const double *pq = (const double *)(smem + TL::OFF_QPOS) + tl;
     const int *pi = (const int *)(smem + TL::OFF_POS_INFO) + tl;
     double *pe = v.pend + tl;
@@ -431,7 +444,8 @@ __device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2V
         int info[SS];
 #pragma unroll
         for (int b = 0; b < SS; b++) {
-            x[b] = px[b * L]; y[b] = py[b * L]; z[b] = pz[b * L]; q[b] = pq[b * L];
+            const double2 xy = pxy[b * L];
+            x[b] = xy.x; y[b] = xy.y; z[b] = pz[b * L]; q[b] = pq[b * L];
             info[b] = (HAS_EXP || ljw) ? pi[b * L] : 0;
         }
         double e = 0.0;
@@ -445,7 +459,7 @@ __device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2V
         *pe = e;                                              // waits for the commit
         dl += on ? e - eold : 0.0;                            // eEnd - eStart from per-neighbour differences
         if (TRACE) { sl += on ? eold : 0.0; el += on ? e : 0.0; }
-        px += SS * L; py += SS * L; pz += SS * L; pq += SS * L; pi += SS * L; pe += L;
+        pxy += SS * L; pz += SS * L; pq += SS * L; pi += SS * L; pe += L;
     }
 }
 
@@ -467,12 +481,13 @@ __device__ __forceinline__ void c2_evaluate_wide(const unsigned char *smem, cons
     // the cached energies this move is measured against (the commit of the previous move is in the cache: the team synchronised)
     double e[M], eold[M];
     bool on[M];
+    const int row_m = (m * (m - 1)) >> 1;                     // packed lower triangle: (lo, hi) sits at hi (hi - 1) / 2 + lo
 #pragma unroll
     for (int k = 0; k < M; k++) {
         const int n = tl + L * k;
         on[k] = (n != m) & (n < nmol);
-        const int lo = n < m ? n : m, hi = n < m ? m : n;
-        eold[k] = v.cache[on[k] ? tri_index(lo, hi) : 0];
+        const int idx = n < m ? row_m + n : ((n * (n - 1)) >> 1) + m;      // (n's own row offset is loop-invariant)
+        eold[k] = v.cache[on[k] ? idx : 0];
         e[k] = 0.0;
     }
 #pragma unroll 1
@@ -554,7 +569,7 @@ __device__ __forceinline__ double c2_total_energy(const unsigned char *smem, con
             const int p = TL::pos_of(xm, a);
             const int infi = TL::pos_info(smem, p);
             const int row = info_type(infi) * sys.row_stride;
-            const double xi = v.xs[p], yi = v.ys[p], zi = v.zs[p];
+            const double xi = v.xy[p].x, yi = v.xy[p].y, zi = v.zs[p];
             const double kqi = K_VALUE * TL::qpos(smem, p);
 #pragma unroll
             for (int k = 0; k < M; k++) {
@@ -568,7 +583,7 @@ __device__ __forceinline__ double c2_total_energy(const unsigned char *smem, con
                         double2 ab = make_double2(0.0, 0.0);
                         if (HAS_EXP) ab = *(const double2 *)(tab_ab + row + cj);
                         // an empty site slot of a shorter particle sits far away with a zero charge and the all-zero column
-                        e[k] = pair_accumulate<HAS_EXP ? 2 : 1>(e[k], v.xs[pj] - xi, v.ys[pj] - yi, v.zs[pj] - zi, 0.0, kqi * TL::qpos(smem, pj), cd, ab);
+                        e[k] = pair_accumulate<HAS_EXP ? 2 : 1>(e[k], v.xy[pj].x - xi, v.xy[pj].y - yi, v.zs[pj] - zi, 0.0, kqi * TL::qpos(smem, pj), cd, ab);
                     }
                 }
             }
@@ -589,7 +604,7 @@ __device__ __forceinline__ void c2_sites_to_global(const C2View &v, double *dst,
 #pragma unroll
     for (int j = 0; j < M * SS; j++) {
         const int p = j * L + tl, i = sys.pos_site[p];
-        if (i >= 0) { dst[3 * i] = v.xs[p]; dst[3 * i + 1] = v.ys[p]; dst[3 * i + 2] = v.zs[p]; }
+        if (i >= 0) { dst[3 * i] = v.xy[p].x; dst[3 * i + 1] = v.xy[p].y; dst[3 * i + 2] = v.zs[p]; }
     }
 }
 
@@ -613,8 +628,7 @@ __device__ __forceinline__ void c2_sites_from_global(const C2View &v, const doub
 #pragma unroll
     for (int j = 0; j < M * SS; j++) {
         const int p = j * L + tl, i = sys.pos_site[p];
-        v.xs[p] = i >= 0 ? src[3 * i] : FAR_AWAY;
-        v.ys[p] = i >= 0 ? src[3 * i + 1] : FAR_AWAY;
+        v.xy[p] = i >= 0 ? make_double2(src[3 * i], src[3 * i + 1]) : make_double2(FAR_AWAY, FAR_AWAY);
         v.zs[p] = i >= 0 ? src[3 * i + 2] : FAR_AWAY;
     }
 }
@@ -739,7 +753,9 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
                 cs->wr[STREAM_M] = gM.wr; cs->wr[STREAM_S] = gS.wr; cs->wr[STREAM_R] = gR.wr;
             }
             C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
-            crew_bar(NT);
+            if (r < 0) crew_bar(NT);                        // plan[0] is written
+            else c2_bar_arrive(C2_BAR_PLAN + ((r + 1) & 1), NT);
+            if (r >= 0) c2_bar_sync(C2_BAR_RES + (r & 1), NT);      // the teams have posted round r
             if (TL::alive(smem, r + 1) == 0) break;
         }
         if (work) asm volatile("cp.async.wait_all;" ::: "memory");       // (the copies in flight are simply dropped: nothing was consumed from them)
@@ -1001,7 +1017,9 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             mode_prev = mode_cur; mode_cur = mode;
             if (lane == 0) TL::alive(smem, r + 1) = (int)any;
             C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
-            crew_bar(NT);
+            if (r < 0) crew_bar(NT);                        // plan[0] is written
+            else c2_bar_arrive(C2_BAR_PLAN + ((r + 1) & 1), NT);
+            if (r >= 0) c2_bar_sync(C2_BAR_RES + (r & 1), NT);      // the teams have posted round r
             if (!any) break;
         }
         C2TM(if (blockIdx.x == 3 && lane == 0) printf("C1: rounds %lld work %lld total/round %lld\n", tm_rounds, tm_work / tm_rounds, (c2_clock() - tm_begin) / tm_rounds);)
@@ -1075,7 +1093,9 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
                 pl->rnd = rnd; pl->thr = thr; pl->grd = grd; pl->sn = sn; pl->cs = csn; pl->axis = axis; pl->nR = nR;
             }
             C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
-            crew_bar(NT);
+            if (r < 0) crew_bar(NT);                        // plan[0] is written
+            else c2_bar_arrive(C2_BAR_PLAN + ((r + 1) & 1), NT);
+            if (r >= 0) c2_bar_sync(C2_BAR_RES + (r & 1), NT);      // the teams have posted round r
             if (TL::alive(smem, r + 1) == 0) break;
         }
         C2TM(if (blockIdx.x == 3 && lane == 0) printf("C2: rounds %lld work %lld\n", tm_rounds, tm_work / tm_rounds);)
@@ -1091,12 +1111,21 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
         C2Pending pend;
         pend.tx = pend.ty = pend.tz = pend.cx = pend.cy = pend.cz = 0.0;
         pend.pp = -1; pend.pm = -1; pend.m = -1;
+        // this lane's charges: chain-independent, in registers for the whole launch (wide evaluation only)
+        constexpr int WN = (M * SS <= C2_WIDE_MAX) ? M * SS : 1;
+        double wq[WN];
+#pragma unroll
+        for (int j = 0; j < WN; j++) wq[j] = TL::qpos(smem, j * L + tl);
         double last_dE = 0.0;
         int last_oob = 0;
         crew_bar(NT);                                       // "rings filled"
         crew_bar(NT);                                       // plan[0] is written
         C2TM(long long tm_work = 0, tm_rounds = 0, tm_a = 0, tm_b = 0;)
+        // Start the two energy warps of an SM sub-partition (warp ids w and w + 4) half an evaluation apart: nothing re-aligns them
+        // (they only wait for the control warps), and their FP64 bursts overlap less (measured: + 3 %).
+        if ((warp >> 2) & 1) { const long long t0 = clock64(); while (clock64() - t0 < 1000) { } }
         for (int r = 0;; r++) {
+            if (r > 0) c2_bar_sync(C2_BAR_PLAN + (r & 1), NT);      // plan r is posted
             if (TL::alive(smem, r) == 0) break;
             C2TM(const long long tm0 = c2_clock();)
             const C2Plan *pl = &cs->plan[r & 1];
@@ -1109,10 +1138,9 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             const C2Cand d = pl->cand[which];
             int m = -1, sm = 0, lj = 0, commit = 0;
             const int m_prev = pend.m;
-            constexpr int WN = (M * SS <= C2_WIDE_MAX) ? M * SS : 1;
-            double wx[WN], wy[WN], wz[WN], wq[WN];
+            double wx[WN], wy[WN], wz[WN];
 #pragma unroll
-            for (int j = 0; j < WN; j++) wx[j] = wy[j] = wz[j] = wq[j] = 0.0;
+            for (int j = 0; j < WN; j++) wx[j] = wy[j] = wz[j] = 0.0;     // (dead stores: every path that reads them loads them first)
             bool oob = false;
             if (mode != PLAN_IDLE) {
                 const int flags = hdr.y;
@@ -1124,37 +1152,39 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
                 }
                 if (commit) {
                     // setTemps (Molecule.java:128-135) of the move staged last, and its per-neighbour energies into the pair cache
-                    if (pend.pp >= 0) { v.xs[pend.pp] = pend.tx; v.ys[pend.pp] = pend.ty; v.zs[pend.pp] = pend.tz; }
+                    if (pend.pp >= 0) { v.xy[pend.pp] = make_double2(pend.tx, pend.ty); v.zs[pend.pp] = pend.tz; }
                     if (tl == 0 && pend.pm >= 0) { v.com[3 * pend.pm] = pend.cx; v.com[3 * pend.pm + 1] = pend.cy; v.com[3 * pend.pm + 2] = pend.cz; }
                     if constexpr (M * SS <= C2_WIDE_MAX) {
+                        const int row_p = (m_prev * (m_prev - 1)) >> 1;
 #pragma unroll
                         for (int k = 0; k < M; k++) {
                             const int n = tl + L * k;
-                            if ((n != m_prev) & (n < sys.n_mol)) v.cache[tri_index(n < m_prev ? n : m_prev, n < m_prev ? m_prev : n)] = v.pend[k * L + tl];
+                            if ((n != m_prev) & (n < sys.n_mol)) v.cache[n < m_prev ? row_p + n : ((n * (n - 1)) >> 1) + m_prev] = v.pend[k * L + tl];
                         }
                     } else c2_commit_cache<L, M>(v, sys.n_mol, m_prev, tl);
                 }
-                __syncwarp(mask);
-                if (moving) {
-                    // this lane's own coordinates and charges: the loads fly while the trial geometry is built (the slot of the moved
-                    // particle itself is discarded, so the rotateTemp round trip below does not matter here)
-                    if constexpr (M * SS <= C2_WIDE_MAX) {
-#pragma unroll
-                        for (int j = 0; j < WN; j++) {
-                            wx[j] = v.xs[j * L + tl]; wy[j] = v.ys[j * L + tl]; wz[j] = v.zs[j * L + tl]; wq[j] = TL::qpos(smem, j * L + tl);
-                        }
-                    }
-                    m = d.m; sm = d.info & 0xff;
-                    oob = c2_geometry<L, M, SS>(smem, v, sys, d, pl, tl, pend, lj);
-                    // a team with fewer staged sites than another team of the warp: neutral entries up to the common bound
-                    if (tl >= sm && tl < SS) {
-                        C2Stage st;
-                        st.nx = st.ny = st.nz = -FAR_AWAY;       // (not +FAR_AWAY: empty site slots sit there, and r = 0 would give NaN)
-                        st.kq = 0.0; st.row = 0; st.lj = 0; st.pad_[0] = st.pad_[1] = 0;
-                        v.stage[tl] = st;
-                    }
-                } else if (mode == PLAN_TOTAL) c2_total_round<L, M, SS, HAS_EXP>(smem, v, P, chain0 + c, hdr.z, hdr.w, tl, mask);
             }
+            __syncwarp();                                   // the commit is visible to the whole team (all lanes of the warp meet here)
+            // this lane's own coordinates: the loads fly while the trial geometry is built (the slot of the moved particle
+            // itself is discarded, so the rotateTemp round trip below does not matter here)
+            if constexpr (M * SS <= C2_WIDE_MAX) {
+#pragma unroll
+                for (int j = 0; j < WN; j++) {
+                    const double2 xy = v.xy[j * L + tl];
+                    wx[j] = xy.x; wy[j] = xy.y; wz[j] = v.zs[j * L + tl];
+                }
+            }
+            if (moving) {
+                m = d.m; sm = d.info & 0xff;
+                oob = c2_geometry<L, M, SS>(smem, v, sys, d, pl, tl, pend, lj);
+                // a team with fewer staged sites than another team of the warp: neutral entries up to the common bound
+                if (tl >= sm && tl < SS) {
+                    C2Stage st;
+                    st.nx = st.ny = st.nz = -FAR_AWAY;       // (not +FAR_AWAY: empty site slots sit there, and r = 0 would give NaN)
+                    st.kq = 0.0; st.row = 0; st.lj = 0; st.pad_[0] = st.pad_[1] = 0;
+                    v.stage[tl] = st;
+                }
+            } else if (mode == PLAN_TOTAL) c2_total_round<L, M, SS, HAS_EXP>(smem, v, P, chain0 + c, hdr.z, hdr.w, tl, mask);
             C2TM(const long long tma = c2_clock(); tm_a += tma - tm0;)
             // warp-wide: who is out of bounds (per team), the most staged sites of any team, which staged sites are Lennard-Jones
             const unsigned oob_w = __ballot_sync(0xffffffffu, oob);
@@ -1188,7 +1218,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
                 last_dE = 0.0; last_oob = 1;
             }
             C2TM(tm_b += c2_clock() - tma; tm_work += c2_clock() - tm0; tm_rounds++;)
-            crew_bar(NT);
+            c2_bar_arrive(C2_BAR_RES + (r & 1), NT);        // results of round r are posted
         }
         C2TM(if (blockIdx.x == 3 && lane == 0) printf("E%d: rounds %lld work %lld (plan+commit+geometry %lld, evaluate %lld)\n", warp, tm_rounds, tm_work / tm_rounds, tm_a / tm_rounds, tm_b / tm_rounds);)
     }
