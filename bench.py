@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--chains-per-gpu", type=int, default=0)
     ap.add_argument("--moves-per-point", type=int, default=0, help="override Moves per Point (default: shipped 20000)")
     ap.add_argument("--threads-per-chain", type=int, default=0)
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 team kernel, 2 crew kernel (tr_set_kernel)")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 team kernel, 2 crew kernel, 3 crew2 kernel (tr_set_kernel)")
     ap.add_argument("--chains-per-block", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -408,6 +408,15 @@ def run_ours(args):
     # ---- e2e: the host-facing call sequence, host buffers in and out
     h2d = seeds.nbytes + (sidx.nbytes if sidx is not None else 0)
     keep = {}
+    pinned = {}
+
+    def pinned_like(name, shape, dtype):
+        """Caller-owned page-locked result buffers (what a host that cares about transfer time passes to tr_get_*)."""
+        if name not in pinned:
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            pinned[name] = (t, t.numpy().view(dtype).reshape(shape))
+        return pinned[name][1]
 
     def e2e_step():
         flush.zero_()
@@ -418,8 +427,12 @@ def run_ours(args):
         eng.pack_minima_device(minima_dev.data_ptr())
         allmin = gather_minima(minima_dev, world)    # NCCL all-gather of 24 B per chain
         s = eng.summary()
-        pts = eng.points()
-        se, st, sx = eng.snapshots(with_sites=True)  # every write(n) structure: what the host turns into OutputN.xyz
+        n_pts, n_snap = eng.max_points()
+        from transrot_b200 import POINT_DTYPE
+        pts = eng.points(out=pinned_like("pts", (cpg, n_pts), POINT_DTYPE))
+        # every write(n) structure: what the host turns into OutputN.xyz
+        se, st, sx = eng.snapshots(out=(pinned_like("se", (cpg, n_snap), np.float64), pinned_like("st", (cpg, n_snap), np.int32),
+                                        pinned_like("sx", (cpg, n_snap, system.n_sites, 3), np.float64)))
         best = global_minimum(allmin)
         nbytes = allmin.nbytes // world + s.nbytes + pts.nbytes + se.nbytes + st.nbytes + sx.nbytes
         if gather_structs:                           # config #4: every chain's minimum structure on every rank, then to the host

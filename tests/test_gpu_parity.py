@@ -84,9 +84,9 @@ def test_total_and_delta_energy_vs_oracle(engine, dbase, sample_cfg, name):
         mols.append(m); trials.append(t); es_ref.append(es); ee_ref.append(ee)
     got = engine.total_energy(np.stack(structs))
     # 1e-12 of the summed |pair terms| (a dilute start structure has |E| ~ 0.1 from terms summing to ~1e4);
-    # relative to |E| itself the same differences are below 1e-10
+    # relative to |E| itself the same differences stay below 1e-12 even there (profiles/parity_r2.md: 7e-13 at cond 4.7e4)
     assert np.max(np.abs(got - np.array(totals)) / np.array(scales)) <= TOL, (got, totals)
-    assert np.max(rel_err(got, np.array(totals))) <= 1e-10, (got, totals)
+    assert np.max(rel_err(got, np.array(totals))) <= 5e-12, (got, totals)     # observed: <= 7e-13 (profiles/parity_r2.md)
     es, ee, de = engine.delta_energy(np.stack(structs), mols, np.stack(trials))
     es_ref, ee_ref = np.array(es_ref), np.array(ee_ref)
     scale = np.maximum(np.abs(es_ref), np.abs(ee_ref))

@@ -48,32 +48,101 @@ __global__ void com_kernel(DevSystem sys, const double *sites, double *com, long
     center_of_mass(sys, sites + (size_t)chain * sys.n_sites * 3, m, com + ((size_t)chain * sys.n_mol + m) * 3);
 }
 
-// One thread per chain: Main.java:34-37 (fan-out), Main.java:58-60 + Space.java:72-117
-// (propagate with box growth, then the random initial rotation), and the schedule locals of
-// Main.java:178-186.  The initial calcEnergy / write(0) is done by the first anneal launch.
-__global__ void init_chains_kernel(InitParams ip)
+// ---- chain initialisation: one WARP per chain --------------------------------------------------------------------------------
+// Main.java:34-37 (seed fan-out), Main.java:58-60 + Space.java:72-117 (propagate with box growth, then the random initial
+// rotation), and the schedule locals of Main.java:178-186.  The initial calcEnergy / write(0) is done by the first anneal launch.
+//
+// What is serial stays on one lane (MersenneTwister.setSeed is a recurrence; the order of the draws is the reference's), what
+// is not is spread over the warp: the three stream seedings run side by side on three lanes, a 624-word block is regenerated
+// 32 words at a time, an attempted position is tested against the particles placed so far one particle per lane, sites are
+// put and rotated one site per lane, and the stream states leave for global memory in coalesced rows.  The streams live in
+// shared memory while the chain is set up.
+
+constexpr int INIT_WARPS = 4;            // chains per block
+
+// mt[k] of the next block from the current one, in place, by the whole warp: new[k] = (k < 227 ? old[k+397] : new[k-227]) ^
+// twist(old[k], k == 623 ? new[0] : old[k+1]).  Chunks of 32 in ascending order: everything a chunk reads is either still old
+// (k + 1, k + 397 lie in later chunks) or already new (k - 227 lies at least seven chunks back; new[0] for k = 623).
+__device__ __forceinline__ void warp_mt_regen(uint32_t *mt, int lane)
 {
-    const long long chain = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int base = 0; base < MT_N; base += 32) {
+        const int k = base + lane;
+        uint32_t v = 0;
+        if (k < MT_N) {
+            const uint32_t a = mt[k];
+            const uint32_t b = mt[k == MT_N - 1 ? 0 : k + 1];
+            const uint32_t far = mt[k < MT_N - MT_M ? k + MT_M : k + MT_M - MT_N];
+            const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+            v = far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        __syncwarp();
+        if (k < MT_N) mt[k] = v;
+        __syncwarp();
+    }
+}
+
+// MersenneTwister.next(32) for the whole warp (every lane gets the word; mti is warp-uniform).
+__device__ __forceinline__ uint32_t warp_mt_next32(uint32_t *mt, int &mti, int lane)
+{
+    if (mti >= MT_N) { warp_mt_regen(mt, lane); mti = 0; }
+    return mt_temper(mt[mti++]);
+}
+
+__device__ __forceinline__ double warp_mt_next_double(uint32_t *mt, int &mti, int lane)
+{
+    const uint64_t hi = (uint64_t)(warp_mt_next32(mt, mti, lane) >> 6) << 26;
+    const uint64_t lo = warp_mt_next32(mt, mti, lane) >> 6;
+    return (double)(int64_t)(hi | lo) * 0x1.0p-52;
+}
+
+__device__ __forceinline__ int warp_mt_next_int(uint32_t *mt, int &mti, int n, int lane)
+{
+    if ((n & -n) == n) return (int)(((int64_t)n * (int64_t)(warp_mt_next32(mt, mti, lane) >> 1)) >> 31);
+    int bits, val;
+    do {
+        bits = (int)(warp_mt_next32(mt, mti, lane) >> 1);
+        val = bits % n;
+    } while ((int)((uint32_t)bits - (uint32_t)val + (uint32_t)(n - 1)) < 0);
+    return val;
+}
+
+__global__ void __launch_bounds__(32 * INIT_WARPS) init_chains_kernel(InitParams ip)
+{
+    __shared__ uint32_t s_mt[INIT_WARPS][3][MT_N];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long chain = (long long)blockIdx.x * INIT_WARPS + warp;
     if (chain >= ip.n_chains) return;
     const DevSystem &sys = ip.sys;
-    // buffer 0 of each stream's ping-pong pair receives the reference-form state
-    uint32_t *mtM = ip.mt + ((size_t)chain * 3 + STREAM_M) * 2 * MT_N;
-    uint32_t *mtS = ip.mt + ((size_t)chain * 3 + STREAM_S) * 2 * MT_N;
-    uint32_t *mtR = ip.mt + ((size_t)chain * 3 + STREAM_R) * 2 * MT_N;
+    uint32_t *mtM = s_mt[warp][STREAM_M], *mtS = s_mt[warp][STREAM_S], *mtR = s_mt[warp][STREAM_R];
+    // buffer 0 of each stream's ping-pong pair in global memory receives the reference-form state at the end
+    uint32_t *gM = ip.mt + ((size_t)chain * 3 + STREAM_M) * 2 * MT_N;
+    uint32_t *gS = ip.mt + ((size_t)chain * 3 + STREAM_S) * 2 * MT_N;
+    uint32_t *gR = ip.mt + ((size_t)chain * 3 + STREAM_R) * 2 * MT_N;
     int posM = MT_N, posS = MT_N, posR = MT_N;
     if (ip.seeds) {
-        mt_std_seed_long(mtM, ip.seeds[chain]);          // seedGenerator, Main.java:24,34
+        // seedGenerator (Main.java:24,34): one lane seeds it in the M buffer, the warp regenerates, three nextLong()
+        if (lane == 0) mt_std_seed_long(mtM, ip.seeds[chain]);
+        __syncwarp();
         int mti = MT_N;
-        const int64_t sM = mt_std_next_long(mtM, mti);
-        const int64_t sS = mt_std_next_long(mtM, mti);
-        const int64_t sR = mt_std_next_long(mtM, mti);
-        mt_std_seed_long(mtM, sM);                       // Main.setSeed      (Main.java:35)
-        mt_std_seed_long(mtS, sS);                       // Space.setSeed     (Main.java:36)
-        mt_std_seed_long(mtR, sR);                       // Molecule.setSeed  (Main.java:37)
-    } else if (ip.mt_pos) {
-        posM = ip.mt_pos[chain * 3 + STREAM_M];
-        posS = ip.mt_pos[chain * 3 + STREAM_S];
-        posR = ip.mt_pos[chain * 3 + STREAM_R];
+        long long sd[3];
+        for (int i = 0; i < 3; i++) {
+            const uint64_t hi = (uint64_t)warp_mt_next32(mtM, mti, lane) << 32;
+            const uint64_t lo = warp_mt_next32(mtM, mti, lane);
+            sd[i] = (long long)(hi | lo);
+        }
+        __syncwarp();
+        // Main.setSeed / Space.setSeed / Molecule.setSeed (Main.java:35-37), side by side
+        if (lane < 3) mt_std_seed_long(s_mt[warp][lane], lane == 0 ? sd[0] : (lane == 1 ? sd[1] : sd[2]));
+        __syncwarp();
+    } else {
+        for (int s = 0; s < 3; s++)
+            for (int k = lane; k < MT_N; k += 32) s_mt[warp][s][k] = ip.mt[((size_t)chain * 3 + s) * 2 * MT_N + k];
+        if (ip.mt_pos) {
+            posM = ip.mt_pos[chain * 3 + STREAM_M];
+            posS = ip.mt_pos[chain * 3 + STREAM_S];
+            posR = ip.mt_pos[chain * 3 + STREAM_R];
+        }
+        __syncwarp();
     }
 
     double L = ip.space_len;
@@ -84,32 +153,37 @@ __global__ void init_chains_kernel(InitParams ip)
         const int N = sys.n_mol;
         for (;;) {                                        // while (!s.propagate()) spaceLen *= 1.1
             bool failed = false;
-            int placed = 0;
             for (int li = 0; li < N && !failed; li++) {
                 int c = 0;
+                const double rad = sys.mol_radius[li];
                 for (;;) {
                     const double half = __ddiv_rn(L, 2.0);
-                    const double x = __dsub_rn(__dmul_rn(mt_std_next_double(mtS, posS), L), half);
-                    const double y = __dsub_rn(__dmul_rn(mt_std_next_double(mtS, posS), L), half);
-                    const double z = __dsub_rn(__dmul_rn(mt_std_next_double(mtS, posS), L), half);
-                    bool ok = true;
-                    for (int n = 0; n < placed; n++) {
-                        const double mind = __dadd_rn(sys.mol_radius[li], sys.mol_radius[n]);
+                    const double x = __dsub_rn(__dmul_rn(warp_mt_next_double(mtS, posS, lane), L), half);
+                    const double y = __dsub_rn(__dmul_rn(warp_mt_next_double(mtS, posS, lane), L), half);
+                    const double z = __dsub_rn(__dmul_rn(warp_mt_next_double(mtS, posS, lane), L), half);
+                    // Space.java:84-93: too close to a particle placed earlier?  (the reference stops at the first hit; any hit
+                    // fails the attempt, so the particles are tested one per lane)
+                    bool hit = false;
+                    for (int n = lane; n < li; n += 32) {
+                        const double mind = __dadd_rn(rad, sys.mol_radius[n]);
                         const double dx = __dsub_rn(com[3 * n], x), dy = __dsub_rn(com[3 * n + 1], y), dz = __dsub_rn(com[3 * n + 2], z);
                         const double d = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-                        if (d < mind) { c++; ok = false; break; }
+                        hit |= d < mind;
                     }
-                    if (ok) {
-                        // Molecule.put (Molecule.java:51-62)
-                        for (int s = sys.mol_off[li]; s < sys.mol_off[li + 1]; s++) {
+                    if (!__any_sync(0xffffffffu, hit)) {
+                        // Molecule.put (Molecule.java:51-62), one site per lane
+                        const int s0 = sys.mol_off[li], s1 = sys.mol_off[li + 1];
+                        for (int s = s0 + lane; s < s1; s += 32) {
                             sites[3 * s] = __dadd_rn(sys.site_def[3 * s], x);
                             sites[3 * s + 1] = __dadd_rn(sys.site_def[3 * s + 1], y);
                             sites[3 * s + 2] = __dadd_rn(sys.site_def[3 * s + 2], z);
                         }
-                        center_of_mass(sys, sites, li, com + 3 * li);
-                        placed++;
+                        __syncwarp();
+                        if (lane == 0) center_of_mass(sys, sites, li, com + 3 * li);
+                        __syncwarp();
                         break;
                     }
+                    c++;
                     if (c >= ip.max_prop_failures) { failed = true; break; }
                 }
             }
@@ -117,18 +191,18 @@ __global__ void init_chains_kernel(InitParams ip)
             L = __dmul_rn(L, 1.1);
             retries++;
         }
-        // Space.java:110-114: rotateTemp(2*PI) + setTemps for every particle, in space order
+        // Space.java:110-114: rotateTemp(2*PI) + setTemps for every particle, in space order; one site per lane
         for (int m = 0; m < N; m++) {
             const int s0 = sys.mol_off[m], s1 = sys.mol_off[m + 1];
             if (s1 - s0 <= 1) continue;
-            const double u = mt_std_next_double(mtR, posR);
+            const double u = warp_mt_next_double(mtR, posR, lane);
             const double rotAmount = __dmul_rn(__dmul_rn(__dsub_rn(u, 0.5), 2.0), JAVA_TWO_PI);
-            const int axis = mt_std_next_int(mtR, posR, 3);
+            const int axis = warp_mt_next_int(mtR, posR, 3, lane);
             double sn, cs;
             sincos(rotAmount, &sn, &cs);
             const double nsn = __dmul_rn(-1.0, sn);
             const double cx = com[3 * m], cy = com[3 * m + 1], cz = com[3 * m + 2];
-            for (int s = s0; s < s1; s++) {
+            for (int s = s0 + lane; s < s1; s += 32) {
                 const double ax = __dsub_rn(sites[3 * s], cx), ay = __dsub_rn(sites[3 * s + 1], cy), az = __dsub_rn(sites[3 * s + 2], cz);
                 double tx, ty, tz;
                 if (axis == 0) {
@@ -150,24 +224,29 @@ __global__ void init_chains_kernel(InitParams ip)
             }
         }
     }
+    __syncwarp();
+    // the streams leave for global memory in coalesced rows
+    for (int k = lane; k < MT_N; k += 32) { gM[k] = mtM[k]; gS[k] = mtS[k]; gR[k] = mtR[k]; }
 
-    int si = ip.sched_idx ? ip.sched_idx[chain] : 0;
-    if (si < 0 || si >= ip.n_sched) si = 0;
-    const tr_schedule sch = ip.sched[si];
-    ChainCtrl c;
-    memset(&c, 0, sizeof c);
-    c.t = sch.max_temp; c.saveT = sch.max_temp; c.delT = 0.0;
-    c.maxD = sch.max_trans; c.maxRot = sch.max_rot;
-    c.probRot = sch.magwalk_prob_rot; c.probTrans = sch.magwalk_prob_trans;
-    c.space_len = L;
-    c.min_energy = 1.7976931348623157e308;          // Double.MAX_VALUE (Space.java:23)
-    c.ptsPerTooth = sch.static_temp ? 1 : sch.points_per_tooth;   // Main.java:74-76
-    c.sched = si;
-    c.prop_retries = retries;
-    c.rng[STREAM_M].par = 0; c.rng[STREAM_M].gen = MT_N; c.rng[STREAM_M].fed = posM;
-    c.rng[STREAM_S].par = 0; c.rng[STREAM_S].gen = MT_N; c.rng[STREAM_S].fed = posS;
-    c.rng[STREAM_R].par = 0; c.rng[STREAM_R].gen = MT_N; c.rng[STREAM_R].fed = posR;
-    ip.ctrl[chain] = c;
+    if (lane == 0) {
+        int si = ip.sched_idx ? ip.sched_idx[chain] : 0;
+        if (si < 0 || si >= ip.n_sched) si = 0;
+        const tr_schedule sch = ip.sched[si];
+        ChainCtrl c;
+        memset(&c, 0, sizeof c);
+        c.t = sch.max_temp; c.saveT = sch.max_temp; c.delT = 0.0;
+        c.maxD = sch.max_trans; c.maxRot = sch.max_rot;
+        c.probRot = sch.magwalk_prob_rot; c.probTrans = sch.magwalk_prob_trans;
+        c.space_len = L;
+        c.min_energy = 1.7976931348623157e308;          // Double.MAX_VALUE (Space.java:23)
+        c.ptsPerTooth = sch.static_temp ? 1 : sch.points_per_tooth;   // Main.java:74-76
+        c.sched = si;
+        c.prop_retries = retries;
+        c.rng[STREAM_M].par = 0; c.rng[STREAM_M].gen = MT_N; c.rng[STREAM_M].fed = posM;
+        c.rng[STREAM_S].par = 0; c.rng[STREAM_S].gen = MT_N; c.rng[STREAM_S].fed = posS;
+        c.rng[STREAM_R].par = 0; c.rng[STREAM_R].gen = MT_N; c.rng[STREAM_R].fed = posR;
+        ip.ctrl[chain] = c;
+    }
 }
 
 // ---- probes -----------------------------------------------------------------------------------

@@ -342,9 +342,8 @@ int launch_init(tr_ctx *ctx, const long long *d_seeds, const int *d_sched_idx, c
     ip.max_prop_failures = max_prop_failures;
     ip.propagate = propagate;
     ip.n_sched = (int)ctx->h_sched.size();
-    const int threads = 64;
-    const unsigned blocks = (unsigned)((ctx->pending_chains + threads - 1) / threads);
-    init_chains_kernel<<<blocks, threads, 0, ctx->stream>>>(ip);
+    const unsigned blocks = (unsigned)((ctx->pending_chains + INIT_WARPS - 1) / INIT_WARPS);       // one warp per chain
+    init_chains_kernel<<<blocks, 32 * INIT_WARPS, 0, ctx->stream>>>(ip);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     return TR_OK;

@@ -340,17 +340,28 @@ class Engine:
         self._ck(self.L.tr_max_points(self.h, C.byref(p), C.byref(s)))
         return int(p.value), int(s.value)
 
-    def points(self) -> np.ndarray:
+    def points(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Per-point records [n_chains, max_points].  `out`: a caller-owned buffer of that shape (e.g. page-locked memory, so
+        that the copy runs at full PCIe speed), else a fresh array."""
         cap, _ = self.max_points()
-        out = np.zeros((self.n_chains, cap), dtype=POINT_DTYPE)
+        if out is None:
+            out = np.zeros((self.n_chains, cap), dtype=POINT_DTYPE)
+        assert out.shape == (self.n_chains, cap) and out.dtype == POINT_DTYPE and out.flags.c_contiguous
         self._ck(self.L.tr_get_points(self.h, out.ctypes.data, cap))
         return out
 
-    def snapshots(self, with_sites: bool = True):
+    def snapshots(self, with_sites: bool = True, out=None):
+        """write(n) snapshots: (energy [n_chains, cap], tooth [n_chains, cap], sites [n_chains, cap, S, 3] or None).  `out`: a
+        caller-owned (energy, tooth, sites) triple of those shapes to copy into (e.g. page-locked memory)."""
         _, cap = self.max_points()
-        e = np.zeros((self.n_chains, cap), dtype=np.float64)
-        t = np.zeros((self.n_chains, cap), dtype=np.int32)
-        x = np.zeros((self.n_chains, cap, self.system.n_sites, 3), dtype=np.float64) if with_sites else None
+        if out is not None:
+            e, t, x = out
+            assert e.shape == (self.n_chains, cap) and t.shape == (self.n_chains, cap) and e.dtype == np.float64 and t.dtype == np.int32
+            assert x is None or (x.shape == (self.n_chains, cap, self.system.n_sites, 3) and x.dtype == np.float64 and x.flags.c_contiguous)
+        else:
+            e = np.zeros((self.n_chains, cap), dtype=np.float64)
+            t = np.zeros((self.n_chains, cap), dtype=np.int32)
+            x = np.zeros((self.n_chains, cap, self.system.n_sites, 3), dtype=np.float64) if with_sites else None
         self._ck(self.L.tr_get_snapshots(self.h, e.ctypes.data, t.ctypes.data, _ptr(x), cap))
         return e, t, x
 
