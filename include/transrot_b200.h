@@ -45,7 +45,8 @@ extern "C" {
 #define TR_KERNEL_AUTO 0   /* tr_set_kernel: let the library choose                                          */
 #define TR_KERNEL_TEAM 1   /* team kernel (anneal.cuh): every lane of a chain's team runs the control flow   */
 #define TR_KERNEL_CREW 2   /* warp-specialised kernel (crew.cuh): one control warp + position-major energy teams */
-#define TR_KERNEL_CREW2 3  /* crew2.cuh: two control warps + particle-major teams + pair-energy cache            */
+#define TR_KERNEL_CREW2 3  /* crew2.cuh: three control warps + particle-major teams + pair-energy cache          */
+#define TR_KERNEL_TEAM_PC 4 /* team kernel on particle-major positions with the pair-energy cache in global memory */
 
 #define TR_MAX_MOL_SITES  16    /* sites in one particle                        */
 #define TR_MAX_SITES      1536  /* sites in `space`                             */

@@ -83,6 +83,74 @@ def test_shipped_kernel_whole_run(engine, dbase, sample_cfg, name, n_chains, mpp
     _compare_whole_run(engine, dbase, cfg, seeds)
 
 
+KERNEL_PREFIX = {1: "anneal_kernel<L=32", 3: "crew2_kernel<L=32", 4: "anneal_kernel<L=32"}
+
+
+@pytest.mark.parametrize("kernel", [1, 3, 4], ids=["team", "crew2", "team_pc"])
+@pytest.mark.parametrize("name,n_chains,mpp,per_block", [("nh4cl32", 3, 2000, 0), ("mixed64", 30, 600, 13), ("h2o256", 2, 300, 0)])
+def test_global_pair_cache_kernels_whole_run(engine, dbase, sample_cfg, name, n_chains, mpp, per_block, kernel):
+    """Every kernel family that can run 33 and more particles, forced with tr_set_kernel whatever the automatic choice is: the
+    plain team kernel (TR_KERNEL_TEAM), and the two that keep the pair-energy cache in global memory - the crew2 variants with
+    whole-warp teams (TR_KERNEL_CREW2) and the team kernel on particle-major positions (TR_KERNEL_TEAM_PC).  Same whole-run
+    comparison; mixed64 also with many chains per block."""
+    from transrot_b200.engine import TR_KERNEL_AUTO
+    TR_KERNEL_CREW2 = kernel
+
+    cfg = workload_config(sample_cfg, name, movePerPt=mpp, ptsPerTooth=5, numTeeth=2)
+    seeds = [1000 + i for i in range(n_chains)]
+    engine.set_system(system_from_config(dbase, cfg))
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=0)
+    engine.set_kernel(TR_KERNEL_CREW2, per_block)
+    try:
+        engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+        assert engine.kernel_name().startswith(KERNEL_PREFIX[kernel]) and (kernel == 3 or ("pair cache" in engine.kernel_name()) == (kernel == 4))
+        engine.run(0)
+        if n_chains <= 4:
+            _compare_whole_run(engine, dbase, cfg, seeds)
+        else:
+            summ, pts, rng = engine.summary(), engine.points(), engine.rng_state()
+            assert summ["done"].all() and (summ["moves"] == cfg.total_moves()).all()
+            for i in (0, 12, 13, 29):
+                sp = oracle_start(dbase, cfg, seeds[i])
+                res = sp.sawtooth_anneal(sp.write_snapshot(0), points_cap=cfg.num_points() + 2, snap_cap=4)
+                p = pts[i, : len(res.points)]
+                assert np.array_equal(p["accepted"], res.points["accepted"]) and np.array_equal(p["total"], res.points["total"])
+                assert np.array_equal(rng[i], sp.rng_state())
+    finally:
+        engine.set_kernel(TR_KERNEL_AUTO)
+
+
+@pytest.mark.parametrize("kernel", [1, 3, 4], ids=["team", "crew2", "team_pc"])
+@pytest.mark.parametrize("name,n_chains,n_moves", [("nh4cl32", 2, 6000), ("mixed64", 2, 6000), ("h2o256", 2, 1500)])
+def test_global_pair_cache_kernels_decision_trace(engine, dbase, sample_cfg, name, n_chains, n_moves, kernel):
+    """Per-move decision trace of the same kernels (eStart from the global-memory pair cache) against the oracle."""
+    from helpers import compare_traces
+    from transrot_b200.engine import TR_KERNEL_AUTO
+    TR_KERNEL_CREW2 = kernel
+
+    cfg = workload_config(sample_cfg, name, movePerPt=max(n_moves // 4, 1), ptsPerTooth=5, numTeeth=2, maxTemp=600.0)
+    seeds = [1000 + i for i in range(n_chains)]
+    engine.set_system(system_from_config(dbase, cfg))
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=n_moves)
+    engine.set_kernel(TR_KERNEL_CREW2)
+    try:
+        engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+        engine.run(n_moves)
+        engine.synchronize()
+        tr = engine.trace()
+    finally:
+        engine.set_kernel(TR_KERNEL_AUTO)
+        engine.set_options(trace_moves=0)
+    for i, seed in enumerate(seeds):
+        sp = oracle_start(dbase, cfg, seed)
+        res = sp.sawtooth_anneal(sp.calc_energy(), trace_cap=n_moves)
+        first, err_rel, err_cond = compare_traces(tr[i], res.trace, res.trace_abs)
+        assert first == -1, f"chain {i}: decisions diverge at step {first}: gpu={tr[i][first]} oracle={res.trace[first]}"
+        assert err_cond <= 1e-12, err_cond
+
+
 def test_shipped_kernel_full_block_of_chains(engine, dbase, sample_cfg):
     """The launch geometry of the headline run (many chains per block, every energy team busy, several blocks): 300
     (H2O)20 chains, a sample of them against the oracle, all of them against the acceptance statistics' sanity."""
@@ -91,8 +159,12 @@ def test_shipped_kernel_full_block_of_chains(engine, dbase, sample_cfg):
     engine.set_system(system_from_config(dbase, cfg))
     engine.set_schedules(cfg)
     engine.set_options(trace_moves=0)
-    engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
-    engine.run(0)
+    engine.set_kernel(0, 28)          # full blocks, as 4096 chains have them (300 chains alone would spread as 3 per block)
+    try:
+        engine.init_chains_seeded(seeds, cfg.spaceLen, cfg.maxPropFailures)
+        engine.run(0)
+    finally:
+        engine.set_kernel(0)
     summ, pts, rng, mins = engine.summary(), engine.points(), engine.rng_state(), engine.pack_minima()
     assert summ["done"].all() and (summ["moves"] == cfg.total_moves()).all()
     for i in (0, 1, 13, 14, 27, 28, 149, 298, 299):

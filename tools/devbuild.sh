@@ -6,5 +6,5 @@ set -e
 [ -f transrot_b200/build/multi.o ] || python transrot_b200/build.py > /dev/null
 mkdir -p exp_libs
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -DTR_CREW2_DEV "$@" -c transrot_b200/csrc/crew2_launch.cu -o exp_libs/crew2_$name.o
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o exp_libs/lib_$name.so transrot_b200/build/transrot_b200.o transrot_b200/build/crew_launch.o exp_libs/crew2_$name.o transrot_b200/build/multi.o -ldl
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o exp_libs/lib_$name.so transrot_b200/build/transrot_b200.o transrot_b200/build/crew_launch.o exp_libs/crew2_$name.o transrot_b200/build/team_pc_launch.o transrot_b200/build/multi.o -ldl
 echo exp_libs/lib_$name.so

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libtransrot_b200.so")
-SOURCES = ["transrot_b200.cu", "crew_launch.cu", "crew2_launch.cu", "multi.cu"]
+SOURCES = ["transrot_b200.cu", "crew_launch.cu", "crew2_launch.cu", "team_pc_launch.cu", "multi.cu"]
 OBJDIR = os.path.join(HERE, "build")
 
 

@@ -165,13 +165,16 @@ __device__ __forceinline__ bool team_any(bool p, unsigned mask)
 
 __host__ __device__ constexpr int align16(int v) { return (v + 15) & ~15; }
 
-template <int L, int W, int SPL>
+// PC0 > 0 (pair-energy cache form): particle-major positions - thread n % TPC owns particle n as its first (n < TPC) or second
+// particle; the first has PC0 site slots (slots 0 .. PC0-1 of the thread), the second the remaining SPL - PC0.
+template <int L, int W, int SPL, int PC0 = 0>
 struct Layout {
     static constexpr int TPC = Team<L, W>::TPC;
     static constexpr int CPB = Team<L, W>::CPB;
     static constexpr int NPOS = TPC * SPL;
+    static constexpr int NCOM = PC0 > 0 ? TPC * 2 : NPOS;        // particles a chain can have
     static constexpr int OFF_COM = align16((int)sizeof(ChainSmem));
-    static constexpr int OFF_SITES = OFF_COM + align16(NPOS * 24);
+    static constexpr int OFF_SITES = OFF_COM + align16(NCOM * 24);
     static constexpr int CHAIN_BYTES = OFF_SITES + NPOS * (int)sizeof(SiteRec);
     static constexpr int OFF_MOL_OFF = CPB * CHAIN_BYTES;
     static constexpr int OFF_MOVEABLE = OFF_MOL_OFF + align16((NPOS + 1) * 4);
@@ -384,6 +387,199 @@ __device__ __forceinline__ double team_total_energy(const unsigned char *smem, C
     return team_sum<L, W>(acc, cs->part, warp, lane, mask);
 }
 
+// One staged site (trial position only) against SS site slots of one particle of this thread (particle-major layouts: the
+// kernels with a pair-energy cache, crew2.cuh and the PC0 > 0 form of anneal_kernel): SS evaluations written
+// operation by operation across the group (independent dependency chains for the 8-cycle FP64 latency), summed into e.
+// `lj`: the staged site carries Lennard-Jones parameters in some team of the warp (warp-uniform); then the site slots named by
+// `ljb` add the r^-6 / r^-12 terms (every slot, with the Born-Mayer term, when HAS_EXP).
+template <int SS, bool HAS_EXP>
+__device__ __forceinline__ double trial_site_energy(double nx, double ny, double nz, double kq, int row, bool lj, const unsigned char *tab_cd,
+                                          const unsigned char *tab_ab, const double *x, const double *y, const double *z, const double *q,
+                                          const int *info, unsigned ljb, double e)
+{
+    double r2[SS], y0[SS], t[SS], u[SS], p[SS], ri[SS];
+#pragma unroll
+    for (int j = 0; j < SS; j++) { const double d = x[j] - nx; r2[j] = d * d; }
+#pragma unroll
+    for (int j = 0; j < SS; j++) { const double d = y[j] - ny; r2[j] = fma(d, d, r2[j]); }
+#pragma unroll
+    for (int j = 0; j < SS; j++) { const double d = z[j] - nz; r2[j] = fma(d, d, r2[j]); }
+#pragma unroll
+    for (int j = 0; j < SS; j++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[j]) : "d"(r2[j]));
+#pragma unroll
+    for (int j = 0; j < SS; j++) t[j] = r2[j] * y0[j];
+#pragma unroll
+    for (int j = 0; j < SS; j++) u[j] = fma(-t[j], y0[j], 1.0);
+#pragma unroll
+    for (int j = 0; j < SS; j++) p[j] = fma(u[j], 0.375, 0.5);
+#pragma unroll
+    for (int j = 0; j < SS; j++) u[j] = y0[j] * u[j];
+#pragma unroll
+    for (int j = 0; j < SS; j++) ri[j] = fma(p[j], u[j], y0[j]);
+#pragma unroll
+    for (int j = 0; j < SS; j++) e = fma(kq * q[j], ri[j], e);
+    if (HAS_EXP || lj) {
+#pragma unroll
+        for (int j = 0; j < SS; j++) {
+            if (HAS_EXP || ((ljb >> j) & 1u)) {
+                const int cj = info_col(info[j]);
+                const double2 cd = *(const double2 *)(tab_cd + row + cj);
+                const double i2 = ri[j] * ri[j];
+                const double i6 = i2 * i2 * i2;
+                e = fma(fma(cd.y, i6, -cd.x), i6, e);                  // + D/r^12 - C/r^6
+                if (HAS_EXP) {
+                    const double2 ab = *(const double2 *)(tab_ab + row + cj);
+                    e = fma(ab.x, exp(-ab.y * (r2[j] * ri[j])), e);
+                }
+            }
+        }
+    }
+    return e;
+}
+
+// ---- the pair-energy cache form of the team kernel (PC0 > 0: two particles per thread) ------------------------------------------
+// The reference recomputes eStart = sum_n m.calcEnergy(n) for every move (Space.java:711-713) although nothing moved since
+// those pair energies were last formed.  With particle-major positions every particle-pair energy E(m, n) is a plain
+// per-thread sum (the thread that owns n), so a chain keeps all of them (packed lower triangle, global memory / L2,
+// KParams::pair_cache): a move evaluates the TRIAL positions only, reads eStart from the cache, and an accepted move writes its
+// per-neighbour energies back.  Entries are overwritten, never accumulated; every Space.calcEnergy rebuilds them.  A rejected
+// rotation still applies rotateTemp's (a.x - x) + x round trip to the committed coordinates (Molecule.java:70-72,90-92): the
+// entries of that particle then describe coordinates that differ by at most one ulp, once (the round trip is idempotent).
+__host__ __device__ __forceinline__ int pair_cache_count(int n_mol) { return (n_mol * (n_mol - 1) / 2 + 1) & ~1; }
+__device__ __forceinline__ int pair_cache_index(int m, int n) { return n < m ? ((m * (m - 1)) >> 1) + n : ((n * (n - 1)) >> 1) + m; }
+
+// All N0 + N1 site slots of this thread (its first particle's N0, its second particle's N1) against the staged sites, one staged
+// site at a time in a real loop with N0 + N1 independent evaluations in flight; one accumulator per site slot, summed per
+// particle at the end.  `ljb`: site slots that hold a Lennard-Jones site in any particle (team-uniform).
+template <int N0, int N1, bool HAS_EXP>
+__device__ __forceinline__ void trial_energy_two(const StageSite *stage, int sm, unsigned ljb, const unsigned char *tab_cd, const unsigned char *tab_ab,
+                                                 const double (&x)[N0 + N1], const double (&y)[N0 + N1], const double (&z)[N0 + N1],
+                                                 const double (&q)[N0 + N1], const int (&col)[N0 + N1], double &e0, double &e1)
+{
+    constexpr int N = N0 + N1;
+    double es[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) es[j] = 0.0;
+#pragma unroll 1
+    for (int a = 0; a < sm; a++) {
+        const StageSite *st = stage + a;
+        const double nx = st->nx, ny = st->ny, nz = st->nz, kq = st->kq;
+        double r2[N], y0[N], t[N], u[N], p[N], ri[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) { const double d = x[j] - nx; r2[j] = d * d; }
+#pragma unroll
+        for (int j = 0; j < N; j++) { const double d = y[j] - ny; r2[j] = fma(d, d, r2[j]); }
+#pragma unroll
+        for (int j = 0; j < N; j++) { const double d = z[j] - nz; r2[j] = fma(d, d, r2[j]); }
+#pragma unroll
+        for (int j = 0; j < N; j++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[j]) : "d"(r2[j]));
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = r2[j] * y0[j];
+#pragma unroll
+        for (int j = 0; j < N; j++) u[j] = fma(-t[j], y0[j], 1.0);
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = fma(u[j], 0.375, 0.5);
+#pragma unroll
+        for (int j = 0; j < N; j++) u[j] = y0[j] * u[j];
+#pragma unroll
+        for (int j = 0; j < N; j++) ri[j] = fma(p[j], u[j], y0[j]);
+#pragma unroll
+        for (int j = 0; j < N; j++) es[j] = fma(kq * q[j], ri[j], es[j]);
+        if (HAS_EXP || st->lj) {
+            const int row = st->row;
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                if (HAS_EXP || ((ljb >> j) & 1u)) {
+                    const double2 cd = *(const double2 *)(tab_cd + row + col[j]);
+                    const double i2 = ri[j] * ri[j];
+                    const double i6 = i2 * i2 * i2;
+                    es[j] = fma(fma(cd.y, i6, -cd.x), i6, es[j]);                  // + D/r^12 - C/r^6
+                    if (HAS_EXP) {
+                        const double2 ab = *(const double2 *)(tab_ab + row + col[j]);
+                        es[j] = fma(ab.x, exp(-ab.y * (r2[j] * ri[j])), es[j]);
+                    }
+                }
+            }
+        }
+    }
+    e0 = 0.0; e1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < N0; j++) e0 += es[j];
+#pragma unroll
+    for (int j = N0; j < N; j++) e1 += es[j];
+}
+
+// This thread's parts of eStart (from the cache) and eEnd (evaluated) for the particle staged in cs->stage; `pend` keeps the
+// per-neighbour energies for the commit.  The thread that owns m itself evaluates r = 0 garbage for that particle's slots and
+// discards it; empty site slots (a shorter particle, no particle) sit far away with a zero charge and the all-zero column.
+template <int TPC, int N0, int N1, bool HAS_EXP>
+__device__ __forceinline__ void move_energy_cached(const SiteRec *mine, const int (&col)[N0 + N1], const ChainSmem *cs, int sm, int m, int n_mol,
+                                                   unsigned ljb, const unsigned char *tab_cd, const unsigned char *tab_ab, const double *cache, int tid,
+                                                   double (&pend)[2], double &eS, double &eE)
+{
+    // the two cached energies: requested first, consumed after the evaluation (measured against prefetch.global.L1 at the time the
+    // move is drawn + late loads: the early loads are 3-12 % faster)
+    const bool on0 = (tid != m) & (tid < n_mol), on1 = (tid + TPC != m) & (tid + TPC < n_mol);
+    const double old0 = cache[on0 ? pair_cache_index(m, tid) : 0];
+    const double old1 = cache[on1 ? pair_cache_index(m, tid + TPC) : 0];
+    double x[N0 + N1], y[N0 + N1], z[N0 + N1], q[N0 + N1];
+#pragma unroll
+    for (int j = 0; j < N0 + N1; j++) {
+        const SiteRec r = mine[j * TPC];
+        x[j] = r.x; y[j] = r.y; z[j] = r.z; q[j] = r.q;
+    }
+    trial_energy_two<N0, N1, HAS_EXP>(cs->stage, sm, ljb, tab_cd, tab_ab, x, y, z, q, col, pend[0], pend[1]);
+    eE = (on0 ? pend[0] : 0.0) + (on1 ? pend[1] : 0.0);
+    eS = (on0 ? old0 : 0.0) + (on1 ? old1 : 0.0);
+}
+
+// Space.calcEnergy (Space.java:648-658) particle pair by particle pair; every pair energy goes into the cache on the way
+// (this = the lower-indexed particle, as Space.calcEnergy has it).
+template <int L, int W, int SPL, int PC0, bool HAS_EXP>
+__device__ __forceinline__ double team_total_energy_cached(const unsigned char *smem, ChainSmem *cs, const DevSystem &sys, double *cache,
+                                                           int tid, int warp, int lane, unsigned mask)
+{
+    using Lay = Layout<L, W, SPL, PC0>;
+    constexpr int TPC = Lay::TPC;
+    const SiteRec *sites = Lay::sites(cs);
+    const unsigned char *tab_cd = Lay::cd(smem), *tab_ab = Lay::ab(smem, sys);
+    const int nmol = sys.n_mol;
+    double acc = 0.0;
+    for (int xm = 0; xm < nmol; xm++) {
+        const int off = Lay::mol_off(smem, xm), sx = Lay::mol_off(smem, xm + 1) - off;
+        double e[2] = {0.0, 0.0};
+        for (int a = 0; a < sx; a++) {
+            const int p = Lay::site_pos(smem, off + a);
+            const int infi = Lay::pos_info(smem, p);
+            const int row = info_type(infi) * sys.row_stride;
+            const SiteRec ri = sites[p];
+            const double kqi = K_VALUE * ri.q;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int n = tid + TPC * k;
+                if (n > xm && n < nmol) {
+#pragma unroll
+                    for (int j = (k ? PC0 : 0); j < (k ? SPL : PC0); j++) {
+                        const int pj = j * TPC + tid;
+                        const int cj = info_col(Lay::pos_info(smem, pj));
+                        const SiteRec rj = sites[pj];
+                        const double2 cd = *(const double2 *)(tab_cd + row + cj);
+                        double2 ab = make_double2(0.0, 0.0);
+                        if (HAS_EXP) ab = *(const double2 *)(tab_ab + row + cj);
+                        e[k] = pair_accumulate<HAS_EXP ? 2 : 1>(e[k], rj.x - ri.x, rj.y - ri.y, rj.z - ri.z, 0.0, kqi * rj.q, cd, ab);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int n = tid + TPC * k;
+            if (n > xm && n < nmol) { cache[pair_cache_index(xm, n)] = e[k]; acc += e[k]; }
+        }
+    }
+    return team_sum<L, W>(acc, cs->part, warp, lane, mask);
+}
+
 // global [S][3] (site order) <-> shared SiteRec[NPOS] (position order)
 template <int TPC, int NPOS>
 __device__ __forceinline__ void sites_to_global(const SiteRec *sites, double *dst, const DevSystem &sys, int tid)
@@ -410,13 +606,25 @@ __device__ __forceinline__ void sites_from_global(SiteRec *sites, const double *
 
 // write(n) (Space.java:550-623 as far as the device is concerned): calcEnergy, keep the
 // structure, track the minimum (Space.java:614-617).
-template <int L, int W, int SPL, bool HAS_EXP>
+// Space.calcEnergy of the committed structure, in the form the kernel variant keeps its positions in.
+template <int L, int W, int SPL, bool HAS_EXP, int PC0>
+__device__ __forceinline__ double chain_total_energy(const KParams &P, unsigned char *smem, long long chain, int team, int tid, int warp, int lane,
+                                                     unsigned mask)
+{
+    ChainSmem *cs = Layout<L, W, SPL, PC0>::chain(smem, team);
+    if constexpr (PC0 > 0)
+        return team_total_energy_cached<L, W, SPL, PC0, HAS_EXP>(smem, cs, P.sys, P.pair_cache + (size_t)chain * pair_cache_count(P.sys.n_mol), tid, warp,
+                                                                 lane, mask);
+    else return team_total_energy<L, W, SPL, HAS_EXP>(smem, cs, P.sys, tid, warp, lane, mask);
+}
+
+template <int L, int W, int SPL, bool HAS_EXP, int PC0 = 0>
 __device__ __noinline__ double snapshot(const KParams &P, unsigned char *smem, long long chain, int team, int n,
                                         int tid, int warp, int lane, unsigned mask)
 {
-    using Lay = Layout<L, W, SPL>;
+    using Lay = Layout<L, W, SPL, PC0>;
     ChainSmem *cs = Lay::chain(smem, team);
-    const double e = team_total_energy<L, W, SPL, HAS_EXP>(smem, cs, P.sys, tid, warp, lane, mask);
+    const double e = chain_total_energy<L, W, SPL, HAS_EXP, PC0>(P, smem, chain, team, tid, warp, lane, mask);
     ChainCtrl *c = &cs->ctrl;
     const int k = c->n_snaps;
     if (k < P.max_snaps) {
@@ -446,11 +654,11 @@ __device__ __forceinline__ void refresh_derived(ChainSmem *cs)
 
 // End of a point (Main.java:225-240) and, when it was the last one, end of the tooth (:242-257).
 // Returns true when the chain has finished.  Rare (once per movePerPt moves): kept out of line.
-template <int L, int W, int SPL, bool HAS_EXP>
+template <int L, int W, int SPL, bool HAS_EXP, int PC0 = 0>
 __device__ __noinline__ bool end_of_point(const KParams &P, unsigned char *smem, long long chain, int team,
                                           int tid, int warp, int lane, unsigned mask)
 {
-    using Lay = Layout<L, W, SPL>;
+    using Lay = Layout<L, W, SPL, PC0>;
     ChainSmem *cs = Lay::chain(smem, team);
     ChainCtrl *c = &cs->ctrl;
     const tr_schedule &sch = cs->sch;
@@ -466,7 +674,7 @@ __device__ __noinline__ bool end_of_point(const KParams &P, unsigned char *smem,
             if (t_next < 0.0) t_next = 0.0;
         }
         double me = __longlong_as_double(0x7ff8000000000000LL);
-        if (movie && P.points) me = team_total_energy<L, W, SPL, HAS_EXP>(smem, cs, P.sys, tid, warp, lane, mask);
+        if (movie && P.points) me = chain_total_energy<L, W, SPL, HAS_EXP, PC0>(P, smem, chain, team, tid, warp, lane, mask);
         if (movie && P.movie_sites && pi < P.max_points)          // the frame writeMovie appends (Space.java:740-790)
             sites_to_global<Lay::TPC, Lay::NPOS>(Lay::sites(cs), P.movie_sites + ((size_t)chain * P.max_points + pi) * (size_t)P.sys.n_sites * 3,
                                                  P.sys, tid);
@@ -509,7 +717,7 @@ __device__ __noinline__ bool end_of_point(const KParams &P, unsigned char *smem,
     }
     team_sync<L, W>(mask);
     if (!start_finale) {
-        snapshot<L, W, SPL, HAS_EXP>(P, smem, chain, team, x + 1, tid, warp, lane, mask);   // write(x+1)
+        snapshot<L, W, SPL, HAS_EXP, PC0>(P, smem, chain, team, x + 1, tid, warp, lane, mask);   // write(x+1)
         if (c->x >= numTeeth) {
             if (tid == 0) c->done = 1;
             team_sync<L, W>(mask);
@@ -528,10 +736,11 @@ __device__ __noinline__ int refill_stream(ChainSmem *cs, int stream, int wr, int
     return mt_ring_refill_words<L>(cs->mt + stream * 2 * MT_N, cs->ring[stream], &cs->ctrl.rng[stream], wr, tl, mask);
 }
 
-template <int L, int W, int SPL, int LJS, bool HAS_EXP, bool TRACE, int MINB>
+template <int L, int W, int SPL, int LJS, bool HAS_EXP, bool TRACE, int MINB, int PC0 = 0>
 __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const __grid_constant__ KParams P)
 {
-    using Lay = Layout<L, W, SPL>;
+    using Lay = Layout<L, W, SPL, PC0>;
+    static_assert(PC0 >= 0 && PC0 < SPL, "site slots of the first particle, of the second");
     constexpr int TPC = Lay::TPC;
     constexpr int CPB = Lay::CPB;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -577,12 +786,27 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
     int info[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; k++) info[k] = Lay::pos_info(smem, tid + k * TPC);
+    // pair-energy cache form: this chain's cache, the table columns of this thread's site slots, the site slots that hold
+    // Lennard-Jones sites in any particle (team-uniform), and the per-neighbour energies of the move in flight
+    double *cache = nullptr;
+    unsigned ljb = 0;
+    double pend[2] = {0.0, 0.0};
+    int col[SPL];
+    if constexpr (PC0 > 0) {
+        cache = P.pair_cache + (size_t)ch * pair_cache_count(sys.n_mol);
+#pragma unroll
+        for (int k = 0; k < SPL; k++) col[k] = info_col(info[k]);
+        for (int p = 0; p < Lay::NPOS; p++) {
+            const int inf = Lay::pos_info(smem, p);
+            if (info_valid(inf) && info_lj(inf)) ljb |= 1u << (p / TPC);
+        }
+    }
     // ring cursors: (read slot, unread words) per stream, team-uniform
     int rdM = 0, avM = 0, rdS = 0, avS = 0, rdR = 0, avR = 0;
 
     // Main.java:64,71: write(0) and startingEnergy = calcEnergy()
     if (!c->started) {
-        const double e0 = snapshot<L, W, SPL, HAS_EXP>(P, smem, chain, team, 0, tid, warp, lane, mask);
+        const double e0 = snapshot<L, W, SPL, HAS_EXP, PC0>(P, smem, chain, team, 0, tid, warp, lane, mask);
         if (tid == 0) {
             c->start_energy = e0;
             c->running = e0;
@@ -728,7 +952,9 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
             int acc = 0, drew = 0;
             double eS = 0.0, eE = 0.0, dE = 0.0, rnd = 0.0;
             if (!any_oob) {
-                move_energy<TPC, SPL, LJS, HAS_EXP>(mine, info, cs, sm, m, tab_cd, tab_ab, sys.zero_col, eS, eE);
+                if constexpr (PC0 > 0)
+                    move_energy_cached<TPC, PC0, SPL - PC0, HAS_EXP>(mine, col, cs, sm, m, sys.n_mol, ljb, tab_cd, tab_ab, cache, tid, pend, eS, eE);
+                else move_energy<TPC, SPL, LJS, HAS_EXP>(mine, info, cs, sm, m, tab_cd, tab_ab, sys.zero_col, eS, eE);
                 // eEnd - eStart, differenced per thread before the reduction (less cancellation than
                 // reducing the two ~100x larger sums; the reference's own value carries the same rounding noise)
                 dE = team_sum<L, W>(eE - eS, cs->part, warp, lane, mask);
@@ -765,6 +991,13 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
                         com[3 * m + 1] = __dadd_rn(com[3 * m + 1], vb);
                         com[3 * m + 2] = __dadd_rn(com[3 * m + 2], vc);
                     }
+                    if constexpr (PC0 > 0) {  // the pair energies the accepted move left behind
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const int n = tid + TPC * k;
+                            if ((n != m) & (n < sys.n_mol)) cache[pair_cache_index(m, n)] = pend[k];
+                        }
+                    }
                 }
                 evaluated++;
                 sum_sm += (unsigned)sm;
@@ -799,11 +1032,11 @@ __global__ void __launch_bounds__(Team<L, W>::BLOCK, MINB) anneal_kernel(const _
             c->accepted_all += accepted;
             c->moves = moves_before + nz;
             c->evaluated += evaluated;
-            c->pair_evals += 2LL * ((long long)S * sum_sm - sum_sm2);
+            c->pair_evals += (PC0 > 0 ? 1LL : 2LL) * ((long long)S * sum_sm - sum_sm2);     // (eStart comes from the cache)
         }
         team_sync<L, W>(mask);
         if (z < sch.moves_per_point) continue;    // budget exhausted (loop ends) or a capped segment (loop goes on)
-        if (end_of_point<L, W, SPL, HAS_EXP>(P, smem, chain, team, tid, warp, lane, mask)) break;
+        if (end_of_point<L, W, SPL, HAS_EXP, PC0>(P, smem, chain, team, tid, warp, lane, mask)) break;
     }
 #undef RING_NEXT32
 #undef RING_RESERVE

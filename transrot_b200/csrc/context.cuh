@@ -44,6 +44,11 @@ struct PosTables {
 
 // crew2 kernel variant: L lanes per team, M particle slots per lane, SS site slots per particle
 struct Crew2Variant { int L, M, SS; };
+// pair-cache team kernel variant: W warps of L lanes per chain, two particles per thread with N0 and N1 site slots
+struct TeamPcVariant {
+    int L, W, N0, N1;
+    int threads() const { return W > 1 ? 32 * W : L; }
+};
 
 }  // namespace tr
 
@@ -90,8 +95,10 @@ struct tr_ctx {
     int max_points = 0, max_snaps = 0;
     tr::Variant variant{16, 1, 1};
     bool use_crew = false;        // warp-specialised kernel (crew.cuh): automatic choice while a chain fits one warp
-    bool use_crew2 = false;       // crew2.cuh: particle-major teams + pair-energy cache, up to TR_CREW2_MAX_MOL particles
+    bool use_crew2 = false;       // crew2.cuh: particle-major teams + pair-energy cache, see crew2_pick
     tr::Crew2Variant crew2{0, 0, 0};
+    bool use_team_pc = false;     // anneal.cuh with PCM > 0: the team kernel on particle-major positions with the pair-energy cache
+    tr::TeamPcVariant team_pc{0, 0, 0, 0};
     tr::DevBuf<double> d_pair_cache;     // [n_chains][tri_count] particle-pair energies (crew2), part of the chain state
     // tr_set_kernel: 0 = automatic, TR_KERNEL_TEAM / TR_KERNEL_CREW force one family; chains per block / co-resident
     // blocks per SM of the crew kernel (0 = automatic)
@@ -127,10 +134,16 @@ int fail(tr_ctx *ctx, int code, const char *fmt, ...);
 // crew_launch.cu: the warp-specialised kernel family
 int crew_smem_bytes(tr_ctx *ctx, long long n_chains, int *smem);
 int launch_crew(tr_ctx *ctx, const KParams &P);
+// team_pc_launch.cu: the team kernel with the pair-energy cache (TR_KERNEL_TEAM_PC)
+constexpr int TR_TEAM_PC_AUTO_SLOTS = 6;   // ... the automatic choice above TR_CREW2_SMALL_MOL particles up to this many site slots per thread
+bool team_pc_pick(const tr_ctx *ctx, TeamPcVariant *out);
+int team_pc_smem_bytes(tr_ctx *ctx, int *smem, int *pair_count);
+int launch_team_pc(tr_ctx *ctx, const KParams &P);
 // crew2_launch.cu
-constexpr int TR_CREW2_MAX_MOL = 32;
+constexpr bool TR_CREW2_AUTO_BIG = false;   // whole-warp crew2 variants as the automatic choice above 32 particles
+constexpr int TR_CREW2_SMALL_MOL = 32;     // up to here: 8-lane teams, pair cache in shared memory; above: whole-warp teams, cache in global memory
 bool crew2_pick(const tr_ctx *ctx, int max_mol_sites, Crew2Variant *out);
-int crew2_smem_bytes(tr_ctx *ctx, int *smem, int *tri_count);
+int crew2_smem_bytes(tr_ctx *ctx, long long n_chains, int *smem, int *tri_count);
 int launch_crew2(tr_ctx *ctx, const KParams &P);
 
 }  // namespace tr

@@ -27,7 +27,7 @@
 //     from the plan C1 posted a round earlier and from the sign of the previous dE).  C3 is the random-number generator:
 //     it keeps the three MT19937 streams' 128-word rings of tempered words topped up behind the consumers' cursors, four
 //     words at a time - the energy warps no longer spend a sixth of their instructions on ring windows.
-// One named barrier per round over all warps; plans and results are double-buffered by round parity.
+// Plans and results are double-buffered by round parity; see "Round synchronisation" below for the barriers.
 #pragma once
 #include "crew.cuh"
 
@@ -42,12 +42,15 @@ __device__ __forceinline__ long long c2_clock() { long long t; asm volatile("mov
 #endif
 
 // Round synchronisation.  The energy warps and the control warps meet through two pairs of named barriers instead of one
-// block-wide barrier per round, so that an energy warp never waits for ANOTHER ENERGY WARP: it starts round r + 1 as soon as
-// it has finished round r and the control warps have posted plan r + 1 (which they do during round r, from the results of
-// round r - 1).  The control warps start iteration i when every energy warp has posted its results of round i - 1.
+// block-wide barrier per round:
 //   plan barrier p (ids 2, 3; parity of the round the plan is for): control warps ARRIVE after writing the plan, energy warps WAIT.
 //   result barrier p (ids 4, 5; parity of the round): energy warps ARRIVE after posting results, control warps WAIT.
-// Energy warps that share an SM sub-partition drift out of phase this way, and their FP64 bursts stop colliding.
+// So a control warp never blocks on posting a plan and an energy warp never blocks on posting its results: an energy warp starts
+// round r + 1 as soon as every energy warp has finished round r (the barrier counts all of them) and the control warps have
+// posted plan r + 1, which they do during round r from the results of round r - 1.  The energy warps of a block therefore still
+// advance round by round together: a round lasts as long as its slowest energy warp.  That is harmless when every move costs
+// the same ((H2O)20: 7 % of an energy warp's time is spent waiting here) and is what makes the whole-warp variants lose against
+// the team kernels on mixed clusters ((NH4Cl)32: a 5-site move next to 1-site moves; 33 % of all samples wait at the plan barrier).
 __device__ __forceinline__ void c2_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void c2_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 constexpr int C2_BAR_PLAN = 2, C2_BAR_RES = 4;
@@ -105,7 +108,13 @@ struct C2Tables {
     static constexpr int SPL = M * SS;                 // site slots per lane
     static constexpr int NPOS = L * SPL;
     static constexpr int NMOL = L * M;                 // particle slots
-    static constexpr int OFF_MOL_NS = 16;                                      // [0..15]: block-wide scalars
+    // Whole-warp teams (L = 32: 33 or more particles) keep the pair cache in global memory (N (N-1) / 2 doubles per chain no
+    // longer fit beside enough chains to fill an SM: 16 KB at N = 64, 255 KB at N = 256) and evaluate particle slot by
+    // particle slot; small teams keep it in shared memory and evaluate all their site slots at once.
+    static constexpr bool GLOBAL_CACHE = L >= 32;
+    static constexpr bool WIDE = !GLOBAL_CACHE && M * SS <= 10;
+    static constexpr int OFF_SLOT_NS = 16;                                     // [0..15]: block-wide scalars; then [M] ints
+    static constexpr int OFF_MOL_NS = OFF_SLOT_NS + align16(M * 4);
     static constexpr int OFF_MOVEABLE = OFF_MOL_NS + align16(NMOL * 4);
     static constexpr int OFF_POS_INFO = OFF_MOVEABLE + align16(NMOL * 4);
     static constexpr int OFF_QPOS = OFF_POS_INFO + align16(NPOS * 4);
@@ -121,7 +130,7 @@ struct C2Tables {
     static constexpr int T_ZS = T_XY + NPOS * 16;               // [NPOS] double
     static constexpr int T_PEND = T_ZS + NPOS * 8;
     static constexpr int T_CACHE = T_PEND + NMOL * 8;
-    static constexpr int T_END = T_CACHE + ((NMOL * (NMOL - 1) / 2 + 1) & ~1) * 8;
+    static constexpr int T_END = T_CACHE + (GLOBAL_CACHE ? 0 : ((NMOL * (NMOL - 1) / 2 + 1) & ~1) * 8);
     // control region: 16 mod 128 bytes, so that the lanes of a control warp (one chain each) spread over the banks
     __host__ __device__ static constexpr int ctrl_bytes() { return ((align16((int)sizeof(C2Chain)) + 127) & ~127) + 16; }
     // team region: 64 mod 128 bytes, so that the two teams a 64-bit access serves in one pass (8 lanes x 8 bytes each) fall
@@ -129,6 +138,8 @@ struct C2Tables {
     __host__ __device__ static constexpr int team_bytes() { return ((T_END + 127) & ~127) + 64; }
 
     __device__ static __forceinline__ int &alive(unsigned char *smem, int round) { return ((int *)smem)[round & 1]; }
+    // the most sites any lane's particle has in particle slot k (warp-uniform loop bounds for the slot-by-slot evaluation)
+    __device__ static __forceinline__ int slot_ns(const unsigned char *smem, int k) { return *(const int *)(smem + OFF_SLOT_NS + 4 * k); }
     __device__ static __forceinline__ int mol_ns(const unsigned char *smem, int m) { return *(const int *)(smem + OFF_MOL_NS + 4 * m); }
     __device__ static __forceinline__ int moveable(const unsigned char *smem, int i) { return *(const int *)(smem + OFF_MOVEABLE + 4 * i); }
     __device__ static __forceinline__ int pos_info(const unsigned char *smem, int p) { return *(const int *)(smem + OFF_POS_INFO + 4 * p); }
@@ -153,6 +164,11 @@ struct C2Tables {
         int *ns = (int *)(smem + OFF_MOL_NS), *mv = (int *)(smem + OFF_MOVEABLE), *pi = (int *)(smem + OFF_POS_INFO);
         double *qp = (double *)(smem + OFF_QPOS);
         for (int i = threadIdx.x; i < NMOL; i += blockDim.x) ns[i] = i < sys.n_mol ? sys.mol_off[i + 1] - sys.mol_off[i] : 0;
+        if (threadIdx.x < M) {
+            int most = 0;
+            for (int n = threadIdx.x * L; n < (threadIdx.x + 1) * L && n < sys.n_mol; n++) most = max(most, sys.mol_off[n + 1] - sys.mol_off[n]);
+            *(int *)(smem + OFF_SLOT_NS + 4 * threadIdx.x) = most;
+        }
         for (int i = threadIdx.x; i < sys.n_moveable; i += blockDim.x) mv[i] = sys.moveable[i];
         for (int i = threadIdx.x; i < NPOS; i += blockDim.x) {
             pi[i] = sys.pos_info[i];
@@ -171,10 +187,9 @@ struct C2View {
 
 // Block layout: tables | C control regions | C team regions
 template <int L, int M, int SS>
-__device__ __forceinline__ C2View c2_view(unsigned char *chains, int c, int C, int n_mol)
+__device__ __forceinline__ C2View c2_view(unsigned char *chains, int c, int C, double *global_cache)
 {
     using TL = C2Tables<L, M, SS>;
-    constexpr int NPOS = L * M * SS;
     C2View v;
     v.cs = (C2Chain *)(chains + c * TL::ctrl_bytes());
     unsigned char *b = chains + C * TL::ctrl_bytes() + c * TL::team_bytes();
@@ -182,8 +197,7 @@ __device__ __forceinline__ C2View c2_view(unsigned char *chains, int c, int C, i
     v.com = (double *)(b + TL::T_COM);
     v.xy = (double2 *)(b + TL::T_XY); v.zs = (double *)(b + TL::T_ZS);
     v.pend = (double *)(b + TL::T_PEND);           // [M][L]: per-neighbour energies of the move staged last
-    v.cache = (double *)(b + TL::T_CACHE);
-    (void)n_mol; (void)NPOS;
+    v.cache = TL::GLOBAL_CACHE ? global_cache : (double *)(b + TL::T_CACHE);
     return v;
 }
 
@@ -289,55 +303,6 @@ __device__ __forceinline__ void c2_chunk_finish(C2Gen &g, const uint32_t *slot)
 }
 
 // ---- energy -------------------------------------------------------------------------------------------------------------
-
-// One staged site (trial position) against the SS site slots of one particle slot of this lane: SS evaluations written
-// operation by operation across the group (independent dependency chains for the 8-cycle FP64 latency), summed into e.
-// `lj`: the staged site carries Lennard-Jones parameters in some team of the warp (warp-uniform); then the site slots named by
-// `ljb` add the r^-6 / r^-12 terms (every slot, with the Born-Mayer term, when HAS_EXP).
-template <int SS, bool HAS_EXP>
-__device__ __forceinline__ double c2_site(double nx, double ny, double nz, double kq, int row, bool lj, const unsigned char *tab_cd,
-                                          const unsigned char *tab_ab, const double *x, const double *y, const double *z, const double *q,
-                                          const int *info, unsigned ljb, double e)
-{
-    double r2[SS], y0[SS], t[SS], u[SS], p[SS], ri[SS];
-#pragma unroll
-    for (int j = 0; j < SS; j++) { const double d = x[j] - nx; r2[j] = d * d; }
-#pragma unroll
-    for (int j = 0; j < SS; j++) { const double d = y[j] - ny; r2[j] = fma(d, d, r2[j]); }
-#pragma unroll
-    for (int j = 0; j < SS; j++) { const double d = z[j] - nz; r2[j] = fma(d, d, r2[j]); }
-#pragma unroll
-    for (int j = 0; j < SS; j++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[j]) : "d"(r2[j]));
-#pragma unroll
-    for (int j = 0; j < SS; j++) t[j] = r2[j] * y0[j];
-#pragma unroll
-    for (int j = 0; j < SS; j++) u[j] = fma(-t[j], y0[j], 1.0);
-#pragma unroll
-    for (int j = 0; j < SS; j++) p[j] = fma(u[j], 0.375, 0.5);
-#pragma unroll
-    for (int j = 0; j < SS; j++) u[j] = y0[j] * u[j];
-#pragma unroll
-    for (int j = 0; j < SS; j++) ri[j] = fma(p[j], u[j], y0[j]);
-#pragma unroll
-    for (int j = 0; j < SS; j++) e = fma(kq * q[j], ri[j], e);
-    if (HAS_EXP || lj) {
-#pragma unroll
-        for (int j = 0; j < SS; j++) {
-            if (HAS_EXP || ((ljb >> j) & 1u)) {
-                const int cj = info_col(info[j]);
-                const double2 cd = *(const double2 *)(tab_cd + row + cj);
-                const double i2 = ri[j] * ri[j];
-                const double i6 = i2 * i2 * i2;
-                e = fma(fma(cd.y, i6, -cd.x), i6, e);                  // + D/r^12 - C/r^6
-                if (HAS_EXP) {
-                    const double2 ab = *(const double2 *)(tab_ab + row + cj);
-                    e = fma(ab.x, exp(-ab.y * (r2[j] * ri[j])), e);
-                }
-            }
-        }
-    }
-    return e;
-}
 
 // What a team keeps in registers between rounds to commit the move it staged last (setTemps, Molecule.java:128-135); the
 // per-neighbour energies at the trial position wait in the team's shared-memory region (C2View::pend).
@@ -451,7 +416,7 @@ __device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2V
         double e = 0.0;
 #pragma unroll
         for (int a = 0; a < SS; a++)
-            if (a < sm_w) e = c2_site<SS, HAS_EXP>(snx[a], sny[a], snz[a], skq[a], srow[a], ((ljw >> a) & 1u) != 0u, tab_cd, tab_ab, x, y, z, q, info, ljb, e);
+            if (a < sm_w) e = trial_site_energy<SS, HAS_EXP>(snx[a], sny[a], snz[a], skq[a], srow[a], ((ljw >> a) & 1u) != 0u, tab_cd, tab_ab, x, y, z, q, info, ljb, e);
         const int n = tl + L * k;
         const bool on = (n != m) & (n < nmol);
         const int lo = n < m ? n : m, hi = n < m ? m : n;
@@ -538,6 +503,69 @@ __device__ __forceinline__ void c2_evaluate_wide(const unsigned char *smem, cons
         dl += on[k] ? e[k] - eold[k] : 0.0;                   // eEnd - eStart from per-neighbour differences
         if (TRACE) { sl += on[k] ? eold[k] : 0.0; el += on[k] ? e[k] : 0.0; }
     }
+}
+
+// Whole-warp teams (L = 32): particle slot by particle slot, each against the staged sites in a real loop, with as many site
+// slots in flight as the fullest particle of that slot has sites (warp-uniform: C2Tables::slot_ns) - a slot of single-site ions
+// costs one evaluation per staged site, not SS.  The cached energies come from global memory (L2): all M loads are issued
+// before the first evaluation and are consumed after the last.
+template <int NS, bool HAS_EXP>
+__device__ __forceinline__ double c2_slot_loop(const C2Stage *stage, int sm_w, unsigned ljw, unsigned ljb, const unsigned char *tab_cd, const unsigned char *tab_ab,
+                                               const double *x, const double *y, const double *z, const double *q, const int *info)
+{
+    double e = 0.0;
+#pragma unroll 1
+    for (int a = 0; a < sm_w; a++) {
+        const C2Stage st = stage[a];
+        e = trial_site_energy<NS, HAS_EXP>(st.nx, st.ny, st.nz, st.kq, st.row, ((ljw >> a) & 1u) != 0u, tab_cd, tab_ab, x, y, z, q, info, ljb, e);
+    }
+    return e;
+}
+
+template <int L, int M, int SS, bool HAS_EXP, bool TRACE>
+__device__ __forceinline__ void c2_evaluate_slots(const unsigned char *smem, const C2View &v, const DevSystem &sys, int m, int sm_w, unsigned ljw,
+                                                  unsigned ljb, int tl, double &dl, double &sl, double &el)
+{
+    using TL = C2Tables<L, M, SS>;
+    const unsigned char *tab_cd = TL::cd(smem), *tab_ab = TL::ab(smem, sys);
+    const int nmol = sys.n_mol;
+    const int row_m = (m * (m - 1)) >> 1;
+    double eold[M];
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        const int n = tl + L * k;
+        const bool on = (n != m) & (n < nmol);
+        eold[k] = v.cache[on ? (n < m ? row_m + n : ((n * (n - 1)) >> 1) + m) : 0];
+    }
+    double enew = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < M; k++) {
+        const int ns = TL::slot_ns(smem, k);
+        double x[SS], y[SS], z[SS], q[SS];
+        int info[SS];
+#pragma unroll
+        for (int b = 0; b < SS; b++) {
+            const int p = (k * SS + b) * L + tl;
+            const double2 xy = v.xy[p];
+            x[b] = xy.x; y[b] = xy.y; z[b] = v.zs[p]; q[b] = TL::qpos(smem, p);
+            info[b] = (HAS_EXP || ljw) ? TL::pos_info(smem, p) : 0;
+        }
+        double e;
+        if (SS > 3 && ns > 3) e = c2_slot_loop<SS, HAS_EXP>(v.stage, sm_w, ljw, ljb, tab_cd, tab_ab, x, y, z, q, info);
+        else if (SS > 1 && ns > 1) e = c2_slot_loop<(SS < 3 ? SS : 3), HAS_EXP>(v.stage, sm_w, ljw, ljb, tab_cd, tab_ab, x, y, z, q, info);
+        else e = c2_slot_loop<1, HAS_EXP>(v.stage, sm_w, ljw, ljb, tab_cd, tab_ab, x, y, z, q, info);
+        const int n = tl + L * k;
+        v.pend[k * L + tl] = e;                               // waits for the commit
+        enew += ((n != m) & (n < nmol)) ? e : 0.0;
+    }
+    // this lane's part of eStart from the cache (Space.java:711-713), of eEnd, and their difference
+    double sold = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        const int n = tl + L * k;
+        sold += ((n != m) & (n < nmol)) ? eold[k] : 0.0;
+    }
+    dl = enew - sold; sl = sold; el = enew;
 }
 
 // The pair-cache half of a commit (the energies the accepted move left in C2View::pend), when no evaluation follows it.
@@ -643,6 +671,33 @@ struct C2Pick {                      // the S-stream part of a move starting at 
 
 constexpr int C2_CTRL_WARPS = 3;
 
+// Which warp plays which role.  Warp w runs on SM sub-partition w % 4.  TR_C2_ROLEMAP 0: warps 0, 1, 2 = C1, C2, C3 (one control
+// warp on each of three sub-partitions); 1: warps 0, 1, 4 = C1, C2, C3 (C1 and C3 share sub-partition 0 with one energy warp).
+#ifndef TR_C2_ROLEMAP
+#define TR_C2_ROLEMAP 0
+#endif
+enum { C2_ROLE_C1 = 0, C2_ROLE_C2 = 1, C2_ROLE_C3 = 2, C2_ROLE_E = 3 };
+__device__ __forceinline__ int c2_role(int warp)
+{
+#if TR_C2_ROLEMAP == 1
+    return warp == 0 ? C2_ROLE_C1 : warp == 1 ? C2_ROLE_C2 : warp == 4 ? C2_ROLE_C3 : C2_ROLE_E;
+#elif TR_C2_ROLEMAP == 2
+    return warp == 0 ? C2_ROLE_C1 : warp == 4 ? C2_ROLE_C2 : warp == 8 ? C2_ROLE_C3 : C2_ROLE_E;
+#else
+    return warp < C2_CTRL_WARPS ? warp : C2_ROLE_E;
+#endif
+}
+__device__ __forceinline__ int c2_energy_index(int warp)
+{
+#if TR_C2_ROLEMAP == 1
+    return warp < 4 ? warp - 2 : warp - 3;          // warps 2, 3, 5, 6, 7 ... -> 0, 1, 2, 3, 4 ...
+#elif TR_C2_ROLEMAP == 2
+    return warp < 4 ? warp - 1 : warp < 8 ? warp - 2 : warp - 3;      // warps 1, 2, 3, 5, 6, 7, 9 ... -> 0 .. 6 ...
+#else
+    return warp - C2_CTRL_WARPS;
+#endif
+}
+
 #ifndef TR_CREW2_MINB
 #define TR_CREW2_MINB 1
 #endif
@@ -673,15 +728,17 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
     for (int c0 = warp * TPW; c0 < nloc; c0 += NW * TPW) {
         const int c = c0 + team;
         if (c < nloc) {
-            const C2View v = c2_view<L, M, SS>(chains, c, C, sys.n_mol);
             const long long ch = chain0 + c;
+            const C2View v = c2_view<L, M, SS>(chains, c, C, P.pair_cache + (size_t)ch * ntri);
             const int *src = (const int *)(P.ctrl + ch);
             int *dst = (int *)&v.cs->ctrl;
             for (int i = tl; i < (int)(sizeof(ChainCtrl) / 4); i += L) dst[i] = src[i];
             const double *cg = P.com + (size_t)ch * sys.n_mol * 3;
             for (int i = tl; i < sys.n_mol * 3; i += L) v.com[i] = cg[i];
-            const double *pc = P.pair_cache + (size_t)ch * ntri;
-            for (int i = tl; i < ntri; i += L) v.cache[i] = pc[i];
+            if constexpr (!TL::GLOBAL_CACHE) {
+                const double *pc = P.pair_cache + (size_t)ch * ntri;
+                for (int i = tl; i < ntri; i += L) v.cache[i] = pc[i];
+            }
             c2_sites_from_global<L, M, SS>(v, P.sites + (size_t)ch * sys.n_sites * 3, sys, tl);
             __syncwarp(mask);
             if (tl == 0) {
@@ -696,10 +753,11 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
     }
     __syncthreads();
 
-    if (warp == 2) {
+    const int role = c2_role(warp);
+    if (role == C2_ROLE_C3) {
         // ================================================================ control warp C3: the random-number generator
         const bool mine = lane < nloc;
-        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, sys.n_mol);
+        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, nullptr);
         C2Chain *cs = v.cs;
         C2Gen gM, gS, gR;
         auto open_stream = [&](C2Gen &g, int s) {
@@ -770,12 +828,12 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             };
             park(gM, STREAM_M); park(gS, STREAM_S); park(gR, STREAM_R);
         }
-    } else if (warp == 0) {
+    } else if (role == C2_ROLE_C1) {
         // ================================================================ control warp C1: lane c <-> chain c
         // S stream, bookkeeping, modes.  Iteration r runs while the teams execute round r: it settles what they did in round
         // r - 1, adopts the move of round r, and writes its part of plan[(r + 1) & 1].
         const bool mine = lane < nloc;
-        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, sys.n_mol);
+        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, nullptr);
         C2Chain *cs = v.cs;
         ChainCtrl *c = &cs->ctrl;
         const tr_schedule &sch = cs->sch;
@@ -1025,13 +1083,13 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
         C2TM(if (blockIdx.x == 3 && lane == 0) printf("C1: rounds %lld work %lld total/round %lld\n", tm_rounds, tm_work / tm_rounds, (c2_clock() - tm_begin) / tm_rounds);)
         // park the chain: counters into c (C3 hands the unread ring words back to the stream cursors)
         if (mine && hot) flush_hot();
-    } else if (warp == 1) {
+    } else if (role == C2_ROLE_C2) {
         // ================================================================ control warp C2: lane c <-> chain c
         // Everything transcendental.  Iteration r: (a) which move is in flight in round r follows from the plan C1 posted
         // for it and from the sign of the dE of round r - 1; (b) its Metropolis double and the threshold -kT log(rnd) on dE;
         // (c) the rotation draw of the NEXT move (Molecule.java:67-68) with sincos.  Both go into plan[(r + 1) & 1].
         const bool mine = lane < nloc;
-        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, sys.n_mol);
+        const C2View v = c2_view<L, M, SS>(chains, mine ? lane : 0, C, nullptr);
         C2Chain *cs = v.cs;
         const ChainCtrl *c = &cs->ctrl;
         const FastMod three = fastmod_make(3);
@@ -1101,9 +1159,9 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
         C2TM(if (blockIdx.x == 3 && lane == 0) printf("C2: rounds %lld work %lld\n", tm_rounds, tm_work / tm_rounds);)
     } else {
         // ================================================================ energy warps: one team <-> one chain
-        const int c = (warp - C2_CTRL_WARPS) * TPW + team;
+        const int c = c2_energy_index(warp) * TPW + team;
         const bool has = c < nloc;
-        const C2View v = c2_view<L, M, SS>(chains, has ? c : 0, C, sys.n_mol);
+        const C2View v = c2_view<L, M, SS>(chains, has ? c : 0, C, P.pair_cache + (size_t)(chain0 + (has ? c : 0)) * ntri);
         C2Chain *cs = v.cs;
         unsigned ljb = 0;                                   // site slots b that hold a Lennard-Jones site in ANY particle (block-uniform)
         for (int p = 0; p < TL::NPOS; p++)
@@ -1112,7 +1170,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
         pend.tx = pend.ty = pend.tz = pend.cx = pend.cy = pend.cz = 0.0;
         pend.pp = -1; pend.pm = -1; pend.m = -1;
         // this lane's charges: chain-independent, in registers for the whole launch (wide evaluation only)
-        constexpr int WN = (M * SS <= C2_WIDE_MAX) ? M * SS : 1;
+        constexpr int WN = TL::WIDE ? M * SS : 1;
         double wq[WN];
 #pragma unroll
         for (int j = 0; j < WN; j++) wq[j] = TL::qpos(smem, j * L + tl);
@@ -1154,7 +1212,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
                     // setTemps (Molecule.java:128-135) of the move staged last, and its per-neighbour energies into the pair cache
                     if (pend.pp >= 0) { v.xy[pend.pp] = make_double2(pend.tx, pend.ty); v.zs[pend.pp] = pend.tz; }
                     if (tl == 0 && pend.pm >= 0) { v.com[3 * pend.pm] = pend.cx; v.com[3 * pend.pm + 1] = pend.cy; v.com[3 * pend.pm + 2] = pend.cz; }
-                    if constexpr (M * SS <= C2_WIDE_MAX) {
+                    if constexpr (TL::WIDE) {
                         const int row_p = (m_prev * (m_prev - 1)) >> 1;
 #pragma unroll
                         for (int k = 0; k < M; k++) {
@@ -1167,7 +1225,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             __syncwarp();                                   // the commit is visible to the whole team (all lanes of the warp meet here)
             // this lane's own coordinates: the loads fly while the trial geometry is built (the slot of the moved particle
             // itself is discarded, so the rotateTemp round trip below does not matter here)
-            if constexpr (M * SS <= C2_WIDE_MAX) {
+            if constexpr (TL::WIDE) {
 #pragma unroll
                 for (int j = 0; j < WN; j++) {
                     const double2 xy = v.xy[j * L + tl];
@@ -1199,7 +1257,8 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             if (sm_w > 0) {
                 double dl = 0.0, sl = 0.0, el = 0.0;
                 if (eval) {
-                    if constexpr (M * SS <= C2_WIDE_MAX) c2_evaluate_wide<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, m, sm_w, ljw, ljb, tl, wx, wy, wz, wq, dl, sl, el);
+                    if constexpr (TL::WIDE) c2_evaluate_wide<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, m, sm_w, ljw, ljb, tl, wx, wy, wz, wq, dl, sl, el);
+                    else if constexpr (TL::GLOBAL_CACHE) c2_evaluate_slots<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, m, sm_w, ljw, ljb, tl, dl, sl, el);
                     else c2_evaluate<L, M, SS, HAS_EXP, TRACE>(smem, v, sys, m, sm_w, ljw, ljb, tl, dl, sl, el);
                 }
                 const double dE = crew_team_sum<L>(dl, mask);
@@ -1228,15 +1287,17 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
     for (int c0 = warp * TPW; c0 < nloc; c0 += NW * TPW) {
         const int c = c0 + team;
         if (c >= nloc) continue;
-        const C2View v = c2_view<L, M, SS>(chains, c, C, sys.n_mol);
         const long long ch = chain0 + c;
+        const C2View v = c2_view<L, M, SS>(chains, c, C, P.pair_cache + (size_t)ch * ntri);
         int *dst = (int *)(P.ctrl + ch);
         const int *src = (const int *)&v.cs->ctrl;
         for (int i = tl; i < (int)(sizeof(ChainCtrl) / 4); i += L) dst[i] = src[i];
         double *cg = P.com + (size_t)ch * sys.n_mol * 3;
         for (int i = tl; i < sys.n_mol * 3; i += L) cg[i] = v.com[i];
-        double *pc = P.pair_cache + (size_t)ch * ntri;
-        for (int i = tl; i < ntri; i += L) pc[i] = v.cache[i];
+        if constexpr (!TL::GLOBAL_CACHE) {
+            double *pc = P.pair_cache + (size_t)ch * ntri;
+            for (int i = tl; i < ntri; i += L) pc[i] = v.cache[i];
+        }
         c2_sites_to_global<L, M, SS>(v, P.sites + (size_t)ch * sys.n_sites * 3, sys, tl);
     }
 }

@@ -73,7 +73,8 @@ bool same_variant(const Variant &a, const Variant &b) { return a.L == b.L && a.W
 // Site -> (thread, slot) permutation of a kernel variant into `tabs`, and the DevSystem that carries it.
 // layout 0 (anneal.cuh, crew.cuh): sites with Lennard-Jones parameters first, so that the trailing slots are Coulomb-only
 // for every thread.  layout 1 (crew2.cuh): particle-major - lane n % L owns particle n in its slot n / L, SS site slots each:
-// position of site a of particle n = ((n / L) * SS + a) * L + n % L.
+// position of site a of particle n = ((n / L) * SS + a) * L + n % L.  layout 2 (anneal.cuh with the pair cache): thread
+// n % T owns particle n as its first (n < T, site slots 0 .. N0-1) or second particle (site slots N0 ..): v = {T, N0, N1}.
 int prepare_tables(tr_ctx *ctx, PosTables &tabs, int layout, const Variant &v, int n_pos, DevSystem *out)
 {
     const int S = ctx->sys.n_sites, T = ctx->sys.n_types;
@@ -85,11 +86,16 @@ int prepare_tables(tr_ctx *ctx, PosTables &tabs, int layout, const Variant &v, i
             for (int i = 0; i < S; i++) if (ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
             n_lj = p;
             for (int i = 0; i < S; i++) if (!ctx->h_site_lj[(size_t)i]) pos[(size_t)p++] = i;
-        } else {
+        } else if (layout == 1) {
             const int L = v.L, SS = v.SPL;
             for (int n = 0; n < ctx->sys.n_mol; n++)
                 for (int i = ctx->h_mol_off[(size_t)n]; i < ctx->h_mol_off[(size_t)n + 1]; i++)
                     pos[(size_t)(((n / L) * SS + (i - ctx->h_mol_off[(size_t)n])) * L + n % L)] = i;
+        } else {
+            const int T2 = v.L, N0 = v.W;              // (threads, site slots of the first particle, of the second)
+            for (int n = 0; n < ctx->sys.n_mol; n++)
+                for (int i = ctx->h_mol_off[(size_t)n]; i < ctx->h_mol_off[(size_t)n + 1]; i++)
+                    pos[(size_t)(((n >= T2 ? N0 : 0) + (i - ctx->h_mol_off[(size_t)n])) * T2 + n % T2)] = i;
         }
         for (int q = 0; q < n_pos; q++)
             if (pos[(size_t)q] >= 0) { inv[(size_t)pos[(size_t)q]] = q; pinfo[(size_t)q] = ctx->h_site_info[(size_t)pos[(size_t)q]]; }
@@ -244,26 +250,44 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
     // 65..192 sites the warp-per-chain team kernel is ahead (0.55 vs 0.45 G moves/s on (NH4Cl)32); tr_set_kernel overrides
     ctx->use_crew = ctx->threads_per_chain == 0 && v.W == 1 && ctx->kernel_choice != TR_KERNEL_TEAM &&
                     (v.L == 16 || ctx->kernel_choice == TR_KERNEL_CREW);
-    // up to TR_CREW2_MAX_MOL particles the particle-major kernel with the pair-energy cache takes over (crew2.cuh)
-    ctx->use_crew2 = ctx->threads_per_chain == 0 && (ctx->kernel_choice == TR_KERNEL_AUTO || ctx->kernel_choice == TR_KERNEL_CREW2) &&
+    // the particle-major kernel with the pair-energy cache takes over wherever it has a variant (crew2.cuh)
+    ctx->use_crew2 = ctx->threads_per_chain == 0 && (ctx->kernel_choice == TR_KERNEL_CREW2 || (ctx->kernel_choice == TR_KERNEL_AUTO && TR_CREW2_AUTO_BIG) ||
+                                                      (ctx->kernel_choice == TR_KERNEL_AUTO && ctx->sys.n_mol <= TR_CREW2_SMALL_MOL)) &&
                      crew2_pick(ctx, max_mol_sites_of(ctx), &ctx->crew2);
     NEED(ctx, ctx->use_crew2 || ctx->kernel_choice != TR_KERNEL_CREW2, "Error: no crew2 kernel variant for this system (%d particles, %d sites in the largest)",
+         ctx->sys.n_mol, max_mol_sites_of(ctx));
+    // above that, the team kernel on particle-major positions with the same cache in global memory (anneal.cuh, PC0 > 0): the
+    // automatic choice where it measured faster than the plain team kernel - six site slots per thread, e.g. (NH4Cl)32 as 5 + 1
+    // (594 vs 554 M moves/s) and (H2O)256 as 3 + 3 (144 vs 135); with eight (the mixed 64-particle cluster as 5 + 3: 409 vs 550)
+    // the wider evaluation costs more registers than the halved arithmetic returns.  tr_set_kernel overrides.
+    ctx->use_team_pc = false;
+    if (!ctx->use_crew2 && ctx->threads_per_chain == 0 && (ctx->kernel_choice == TR_KERNEL_TEAM_PC || ctx->kernel_choice == TR_KERNEL_AUTO) &&
+        ctx->sys.n_mol > TR_CREW2_SMALL_MOL && team_pc_pick(ctx, &ctx->team_pc))
+        ctx->use_team_pc = ctx->kernel_choice == TR_KERNEL_TEAM_PC || ctx->team_pc.N0 + ctx->team_pc.N1 <= TR_TEAM_PC_AUTO_SLOTS;
+    NEED(ctx, ctx->use_team_pc || ctx->kernel_choice != TR_KERNEL_TEAM_PC, "Error: no pair-cache team kernel variant for this system (%d particles, %d sites in the largest)",
          ctx->sys.n_mol, max_mol_sites_of(ctx));
     if (ctx->use_crew2) {
         ctx->use_crew = false;
         const Crew2Variant &c2 = ctx->crew2;
         if (int r = prepare_tables(ctx, ctx->run_tabs, 1, Variant{c2.L, c2.M, c2.SS}, c2.L * c2.M * c2.SS, &ctx->run_sys)) return r;
+    } else if (ctx->use_team_pc) {
+        ctx->use_crew = false;
+        const TeamPcVariant &pc = ctx->team_pc;        // (positions: thread n % threads, its first or second particle)
+        if (int r = prepare_tables(ctx, ctx->run_tabs, 2, Variant{pc.threads(), pc.N0, pc.N1}, pc.threads() * (pc.N0 + pc.N1), &ctx->run_sys)) return r;
     } else if (int r = prepare_variant(ctx, ctx->run_tabs, v, &ctx->run_sys)) return r;
     {
         char nm[96];
         if (ctx->use_crew2) snprintf(nm, sizeof nm, "crew2_kernel<L=%d,M=%d,SS=%d>", ctx->crew2.L, ctx->crew2.M, ctx->crew2.SS);
+        else if (ctx->use_team_pc) snprintf(nm, sizeof nm, "anneal_kernel<L=%d,W=%d,SPL=%d+%d,pair cache>", ctx->team_pc.L, ctx->team_pc.W, ctx->team_pc.N0, ctx->team_pc.N1);
         else if (ctx->use_crew) snprintf(nm, sizeof nm, "crew_kernel<L=%d,SPL=%d>", v.L, v.SPL);
         else snprintf(nm, sizeof nm, "anneal_kernel<L=%d,W=%d,SPL=%d>", v.L, v.W, v.SPL);
         ctx->kernel_name = nm;
     }
     int smem = 0, tri = 0;
     if (ctx->use_crew2) {
-        if (int r = crew2_smem_bytes(ctx, &smem, &tri)) return r;
+        if (int r = crew2_smem_bytes(ctx, n_chains, &smem, &tri)) return r;
+    } else if (ctx->use_team_pc) {
+        if (int r = team_pc_smem_bytes(ctx, &smem, &tri)) return r;
     } else if (ctx->use_crew) {
         if (int r = crew_smem_bytes(ctx, n_chains, &smem)) return r;
     } else {
@@ -305,7 +329,7 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
         CK(ctx, ctx->d_points.alloc(C * max_points));
         CK(ctx, cudaMemsetAsync(ctx->d_points.p, 0, C * max_points * sizeof(tr_point_rec), ctx->stream));
     } else ctx->d_points.release();
-    if (ctx->use_crew2) CK(ctx, ctx->d_pair_cache.alloc(C * (size_t)tri)); else ctx->d_pair_cache.release();
+    if (ctx->use_crew2 || ctx->use_team_pc) CK(ctx, ctx->d_pair_cache.alloc(C * (size_t)tri)); else ctx->d_pair_cache.release();
     if (ctx->trace_moves > 0) {
         CK(ctx, ctx->d_trace.alloc(C * (size_t)ctx->trace_moves));
         CK(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, C * (size_t)ctx->trace_moves * sizeof(tr_trace_rec), ctx->stream));
@@ -623,8 +647,8 @@ extern "C" int tr_init_chains_explicit(tr_ctx *ctx, int64_t n_chains, int64_t fi
 extern "C" int tr_set_kernel(tr_ctx *ctx, int32_t kernel, int32_t chains_per_block, int32_t blocks_per_sm)
 {
     if (!ctx) return TR_EINVAL;
-    NEED(ctx, kernel == TR_KERNEL_AUTO || kernel == TR_KERNEL_TEAM || kernel == TR_KERNEL_CREW || kernel == TR_KERNEL_CREW2,
-         "Error: kernel must be TR_KERNEL_AUTO, TR_KERNEL_TEAM, TR_KERNEL_CREW or TR_KERNEL_CREW2");
+    NEED(ctx, kernel == TR_KERNEL_AUTO || kernel == TR_KERNEL_TEAM || kernel == TR_KERNEL_CREW || kernel == TR_KERNEL_CREW2 || kernel == TR_KERNEL_TEAM_PC,
+         "Error: kernel must be TR_KERNEL_AUTO, TR_KERNEL_TEAM, TR_KERNEL_CREW, TR_KERNEL_CREW2 or TR_KERNEL_TEAM_PC");
     NEED(ctx, chains_per_block >= 0 && chains_per_block <= 32 && blocks_per_sm >= 0 && blocks_per_sm <= 8,
          "Error: chains_per_block must be 0..32 and blocks_per_sm 0..8");
     ctx->kernel_choice = kernel;
@@ -683,6 +707,8 @@ extern "C" int tr_run(tr_ctx *ctx, int64_t max_moves)
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->use_crew2) {
         if (int r = launch_crew2(ctx, P)) return r;
+    } else if (ctx->use_team_pc) {
+        if (int r = launch_team_pc(ctx, P)) return r;
     } else if (ctx->use_crew) {
         if (int r = launch_crew(ctx, P)) return r;
     } else {

@@ -115,7 +115,7 @@ _SIGNATURES = {
 }
 _RESTYPES = {"tr_destroy": None, "tr_destroy_multi": None, "tr_multi_chain_range": None, "tr_last_error": C.c_char_p,
              "tr_multi_last_error": C.c_char_p, "tr_kernel_name": C.c_char_p, "tr_multi_ctx": C.c_void_p, "tr_multi_size": C.c_int32}
-TR_KERNEL_AUTO, TR_KERNEL_TEAM, TR_KERNEL_CREW, TR_KERNEL_CREW2 = 0, 1, 2, 3
+TR_KERNEL_AUTO, TR_KERNEL_TEAM, TR_KERNEL_CREW, TR_KERNEL_CREW2, TR_KERNEL_TEAM_PC = 0, 1, 2, 3, 4
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
