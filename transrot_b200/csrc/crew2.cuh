@@ -53,7 +53,35 @@ __device__ __forceinline__ long long c2_clock() { long long t; asm volatile("mov
 // the team kernels on mixed clusters ((NH4Cl)32: a 5-site move next to 1-site moves; 33 % of all samples wait at the plan barrier).
 __device__ __forceinline__ void c2_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void c2_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-constexpr int C2_BAR_PLAN = 2, C2_BAR_RES = 4;
+constexpr int C2_BAR_PLAN = 2, C2_BAR_RES = 4, C2_BAR_PLAN_B = 6;
+
+// Two groups of energy warps (TR_C2_LAG > 0).  Every SM sub-partition hosts two energy warps (ids w and w + 4); started
+// together they reach their FP64-heavy evaluation phase together and share the pipe, then leave it idle together.  Group B
+// (`c2_group(warp) == 1`) has its own plan barrier (ids 6, 7) and starts every round TR_C2_LAG cycles after group A did (a
+// time stamp group A leaves in shared memory), so one group evaluates while the other runs its serial phase.  The control
+// warps arrive at both plan barriers and still wait for the results of all energy warps: plan r + 1 is built from the results
+// of round r - 1, a whole round back, which is what leaves room for the lag.
+// Measured on (H2O)20 x 4096 chains (profiles/r2_experiments.md): lag 0 (one group): 1.51 G moves/s; 600: 1.53; 1000: 1.56;
+// 1400: 1.61; 1800: 1.63; 2200: 1.62; 2600: 1.54 (group A then waits for the plan: lag + group B's round + the control
+// warps' iteration have to fit in two rounds).  The sample cluster (5 site slots per lane, shorter rounds): 1000: 2.02, 1800: 1.97.
+#ifndef TR_C2_LAG
+#define TR_C2_LAG 1800
+#endif
+__device__ __forceinline__ int c2_group(int warp) { return TR_C2_LAG > 0 ? (warp >> 2) & 1 : 0; }
+// threads that meet at a group's plan barrier: the three control warps + the group's energy warps (warps 3 .. NW-1 by role map 0)
+template <int NW>
+__host__ __device__ constexpr int c2_plan_threads(int group)
+{
+    int n = 3;
+    for (int w = 3; w < NW; w++) n += (TR_C2_LAG > 0 ? ((w >> 2) & 1) : 0) == group ? 1 : 0;
+    return 32 * n;
+}
+template <int NW>
+__device__ __forceinline__ void c2_plan_posted(int parity)
+{
+    c2_bar_arrive(C2_BAR_PLAN + parity, c2_plan_threads<NW>(0));
+    if (TR_C2_LAG > 0) c2_bar_arrive(C2_BAR_PLAN_B + parity, c2_plan_threads<NW>(1));
+}
 
 constexpr int C2_RING_NEED_M = 4;      // M words a move consumes, always (Main.java:199-208)
 constexpr int C2_RING_NEED_R = 8;      // R words guaranteed before a move is posted: angle double + up to 6 nextInt(3) tries
@@ -113,7 +141,8 @@ struct C2Tables {
     // particle slot; small teams keep it in shared memory and evaluate all their site slots at once.
     static constexpr bool GLOBAL_CACHE = L >= 32;
     static constexpr bool WIDE = !GLOBAL_CACHE && M * SS <= 10;
-    static constexpr int OFF_SLOT_NS = 16;                                     // [0..15]: block-wide scalars; then [M] ints
+    static constexpr int OFF_STAMP = 16;                                       // [0..15]: block-wide scalars; [16..31]: round stamps
+    static constexpr int OFF_SLOT_NS = 32;                                     // then [M] ints
     static constexpr int OFF_MOL_NS = OFF_SLOT_NS + align16(M * 4);
     static constexpr int OFF_MOVEABLE = OFF_MOL_NS + align16(NMOL * 4);
     static constexpr int OFF_POS_INFO = OFF_MOVEABLE + align16(NMOL * 4);
@@ -138,6 +167,11 @@ struct C2Tables {
     __host__ __device__ static constexpr int team_bytes() { return ((T_END + 127) & ~127) + 64; }
 
     __device__ static __forceinline__ int &alive(unsigned char *smem, int round) { return ((int *)smem)[round & 1]; }
+    // (round << 32 | clock) of the moment group A's first energy warp started the round
+    __device__ static __forceinline__ volatile unsigned long long *stamp(unsigned char *smem, int round)
+    {
+        return (volatile unsigned long long *)(smem + OFF_STAMP) + (round & 1);
+    }
     // the most sites any lane's particle has in particle slot k (warp-uniform loop bounds for the slot-by-slot evaluation)
     __device__ static __forceinline__ int slot_ns(const unsigned char *smem, int k) { return *(const int *)(smem + OFF_SLOT_NS + 4 * k); }
     __device__ static __forceinline__ int mol_ns(const unsigned char *smem, int m) { return *(const int *)(smem + OFF_MOL_NS + 4 * m); }
@@ -433,6 +467,12 @@ __device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2V
 // sites.  Also folds in the pair-cache update of the move committed at the top of this round (`commit_prev`, particle
 // `m_prev`): entry (m_prev, n) is written before entry (m, n) is read, by the lane that owns n.
 constexpr int C2_WIDE_MAX = 10;
+// this lane's charges: in registers for the whole launch, or re-read from shared memory per staged site (frees 2 M SS registers:
+// with the two-group schedule, TR_C2_LAG > 0, the 9-wide evaluation of (H2O)20 otherwise spills)
+#ifndef TR_C2_Q_SMEM
+#define TR_C2_Q_SMEM (TR_C2_LAG > 0)
+#endif
+constexpr bool C2_Q_IN_REGISTERS = !(TR_C2_Q_SMEM);
 
 template <int L, int M, int SS, bool HAS_EXP, bool TRACE>
 __device__ __forceinline__ void c2_evaluate_wide(const unsigned char *smem, const C2View &v, const DevSystem &sys, int m, int sm_w, unsigned ljw,
@@ -478,7 +518,7 @@ __device__ __forceinline__ void c2_evaluate_wide(const unsigned char *smem, cons
 #pragma unroll
         for (int j = 0; j < NE; j++) ri[j] = fma(p[j], u[j], y0[j]);
 #pragma unroll
-        for (int j = 0; j < NE; j++) e[j / SS] = fma(st.kq * q[j], ri[j], e[j / SS]);
+        for (int j = 0; j < NE; j++) e[j / SS] = fma(st.kq * (C2_Q_IN_REGISTERS ? q[j] : TL::qpos(smem, j * L + tl)), ri[j], e[j / SS]);
         if (HAS_EXP || ((ljw >> a) & 1u)) {
 #pragma unroll
             for (int j = 0; j < NE; j++) {
@@ -812,7 +852,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             }
             C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
             if (r < 0) crew_bar(NT);                        // plan[0] is written
-            else c2_bar_arrive(C2_BAR_PLAN + ((r + 1) & 1), NT);
+            else c2_plan_posted<NW>((r + 1) & 1);
             if (r >= 0) c2_bar_sync(C2_BAR_RES + (r & 1), NT);      // the teams have posted round r
             if (TL::alive(smem, r + 1) == 0) break;
         }
@@ -1076,7 +1116,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             if (lane == 0) TL::alive(smem, r + 1) = (int)any;
             C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
             if (r < 0) crew_bar(NT);                        // plan[0] is written
-            else c2_bar_arrive(C2_BAR_PLAN + ((r + 1) & 1), NT);
+            else c2_plan_posted<NW>((r + 1) & 1);
             if (r >= 0) c2_bar_sync(C2_BAR_RES + (r & 1), NT);      // the teams have posted round r
             if (!any) break;
         }
@@ -1152,7 +1192,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             }
             C2TM(tm_work += c2_clock() - tm0; tm_rounds++;)
             if (r < 0) crew_bar(NT);                        // plan[0] is written
-            else c2_bar_arrive(C2_BAR_PLAN + ((r + 1) & 1), NT);
+            else c2_plan_posted<NW>((r + 1) & 1);
             if (r >= 0) c2_bar_sync(C2_BAR_RES + (r & 1), NT);      // the teams have posted round r
             if (TL::alive(smem, r + 1) == 0) break;
         }
@@ -1173,9 +1213,10 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
         constexpr int WN = TL::WIDE ? M * SS : 1;
         double wq[WN];
 #pragma unroll
-        for (int j = 0; j < WN; j++) wq[j] = TL::qpos(smem, j * L + tl);
+        for (int j = 0; j < WN; j++) wq[j] = C2_Q_IN_REGISTERS ? TL::qpos(smem, j * L + tl) : 0.0;
         double last_dE = 0.0;
         int last_oob = 0;
+        const int grp = c2_group(warp);
         crew_bar(NT);                                       // "rings filled"
         crew_bar(NT);                                       // plan[0] is written
         C2TM(long long tm_work = 0, tm_rounds = 0, tm_a = 0, tm_b = 0;)
@@ -1183,8 +1224,18 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
         // (they only wait for the control warps), and their FP64 bursts overlap less (measured: + 3 %).
         if ((warp >> 2) & 1) { const long long t0 = clock64(); while (clock64() - t0 < 1000) { } }
         for (int r = 0;; r++) {
-            if (r > 0) c2_bar_sync(C2_BAR_PLAN + (r & 1), NT);      // plan r is posted
+            if (r > 0) c2_bar_sync(grp ? C2_BAR_PLAN_B + (r & 1) : C2_BAR_PLAN + (r & 1), c2_plan_threads<NW>(grp));      // plan r is posted
             if (TL::alive(smem, r) == 0) break;
+            if (TR_C2_LAG > 0) {
+                if (warp == C2_CTRL_WARPS) {
+                    if (lane == 0) *TL::stamp(smem, r) = ((unsigned long long)(unsigned)r << 32) | (unsigned)clock();
+                } else if (grp) {
+                    unsigned long long st;
+                    do st = *TL::stamp(smem, r); while ((unsigned)(st >> 32) != (unsigned)r);
+                    constexpr unsigned LAG = (M * SS <= 5) ? TR_C2_LAG * 5 / 9 : TR_C2_LAG;      // shorter rounds, shorter lag
+                    while ((unsigned)clock() - (unsigned)st < LAG) { }
+                }
+            }
             C2TM(const long long tm0 = c2_clock();)
             const C2Plan *pl = &cs->plan[r & 1];
             const int4 hdr = *(const int4 *)&pl->mode;       // mode, flags, snap_slot, movie_slot
