@@ -27,6 +27,11 @@
 //     from the plan C1 posted a round earlier and from the sign of the previous dE).  C3 is the random-number generator:
 //     it keeps the three MT19937 streams' 128-word rings of tempered words topped up behind the consumers' cursors, four
 //     words at a time - the energy warps no longer spend a sixth of their instructions on ring windows.
+//   * TWO GROUPS OF ENERGY WARPS half a round apart (TR_C2_LAG): the two energy warps of an SM sub-partition no longer reach
+//     their FP64-heavy evaluation phase together (+ 8 %).
+//   * Clusters of 33 and more particles have variants with whole-warp teams (L = 32) and the pair cache in global memory; they
+//     are correct and tested but lose against the team kernels (a round lasts as long as its slowest energy warp, and a 5-site
+//     move next to 1-site moves leaves most of them waiting), so tr_set_kernel(TR_KERNEL_CREW2) is the only way to get them.
 // Plans and results are double-buffered by round parity; see "Round synchronisation" below for the barriers.
 #pragma once
 #include "crew.cuh"
@@ -155,9 +160,14 @@ struct C2Tables {
     // register per chain serves every access
     static constexpr int T_STAGE = 0;
     static constexpr int T_COM = T_STAGE + SS * (int)sizeof(C2Stage);
-    static constexpr int T_XY = T_COM + align16(NMOL * 24);     // [NPOS] double2 {x, y}: one 16-byte load per site slot
-    static constexpr int T_ZS = T_XY + NPOS * 16;               // [NPOS] double
-    static constexpr int T_PEND = T_ZS + NPOS * 8;
+    // Coordinates: position p sits at element xi(p) = p + p / L - every row of L positions (one site slot of every lane) is
+    // followed by one element of padding, so that the sites of ONE particle (positions L apart: the trial geometry, the commit)
+    // fall into different banks while a team's row stays contiguous.
+    static constexpr int XROW = L + 1;
+    static constexpr int NXY = (NPOS / L) * XROW;
+    static constexpr int T_XY = T_COM + align16(NMOL * 24);     // [NXY] double2 {x, y}: one 16-byte load per site slot
+    static constexpr int T_ZS = T_XY + NXY * 16;                // [NXY] double
+    static constexpr int T_PEND = T_ZS + align16(NXY * 8);
     static constexpr int T_CACHE = T_PEND + NMOL * 8;
     static constexpr int T_END = T_CACHE + (GLOBAL_CACHE ? 0 : ((NMOL * (NMOL - 1) / 2 + 1) & ~1) * 8);
     // control region: 16 mod 128 bytes, so that the lanes of a control warp (one chain each) spread over the banks
@@ -185,6 +195,7 @@ struct C2Tables {
     }
     // position of site a of particle m: particle slot k = m / L of lane m % L
     __device__ static __forceinline__ int pos_of(int m, int a) { return ((m / L) * SS + a) * L + (m % L); }
+    __host__ __device__ static constexpr int xi(int p) { return p + p / L; }
 
     __device__ static void load(unsigned char *smem, const DevSystem &sys)
     {
@@ -362,8 +373,9 @@ __device__ __forceinline__ bool c2_geometry(const unsigned char *smem, const C2V
     if (tl < sm) {
         const int p = TL::pos_of(m, tl);
         const int inf = TL::pos_info(smem, p);
-        const double2 oxy = v.xy[p];
-        double ox = oxy.x, oy = oxy.y, oz = v.zs[p], tx, ty, tz;
+        const int px = TL::xi(p);
+        const double2 oxy = v.xy[px];
+        double ox = oxy.x, oy = oxy.y, oz = v.zs[px], tx, ty, tz;
         if (rot) {
             // Molecule.java:70-95, operation for operation, no contraction
             const double cx = v.com[3 * m], cy = v.com[3 * m + 1], cz = v.com[3 * m + 2];
@@ -381,7 +393,7 @@ __device__ __forceinline__ bool c2_geometry(const unsigned char *smem, const C2V
             ty = axis == 0 ? ru : (axis == 1 ? ay : rw);
             tz = axis == 2 ? az : rw;
             // a.x += x: the committed coordinate keeps the (a.x - x) + x round trip even if the move is rejected
-            v.xy[p] = make_double2(__dadd_rn(ax, cx), __dadd_rn(ay, cy)); v.zs[p] = __dadd_rn(az, cz);
+            v.xy[px] = make_double2(__dadd_rn(ax, cx), __dadd_rn(ay, cy)); v.zs[px] = __dadd_rn(az, cz);
             tx = __dadd_rn(tx, cx); ty = __dadd_rn(ty, cy); tz = __dadd_rn(tz, cz);
         } else {
             tx = __dadd_rn(ox, d.va); ty = __dadd_rn(oy, d.vb); tz = __dadd_rn(oz, d.vc);
@@ -395,7 +407,7 @@ __device__ __forceinline__ bool c2_geometry(const unsigned char *smem, const C2V
         lj_out = st.lj;
         const double b = v.cs->bound;                // t > L*0.75 || t < L*-0.75; the lower bound is the exact negative
         oob = (fabs(tx) > b) | (fabs(ty) > b) | (fabs(tz) > b);
-        pend.tx = tx; pend.ty = ty; pend.tz = tz; pend.pp = p;
+        pend.tx = tx; pend.ty = ty; pend.tz = tz; pend.pp = px;       // (element index, padding included)
     }
     if (tl == 0) {
         pend.pm = rot ? -1 : m;
@@ -443,8 +455,8 @@ __device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2V
         int info[SS];
 #pragma unroll
         for (int b = 0; b < SS; b++) {
-            const double2 xy = pxy[b * L];
-            x[b] = xy.x; y[b] = xy.y; z[b] = pz[b * L]; q[b] = pq[b * L];
+            const double2 xy = pxy[b * TL::XROW];
+            x[b] = xy.x; y[b] = xy.y; z[b] = pz[b * TL::XROW]; q[b] = pq[b * L];
             info[b] = (HAS_EXP || ljw) ? pi[b * L] : 0;
         }
         double e = 0.0;
@@ -458,7 +470,7 @@ __device__ __forceinline__ void c2_evaluate(const unsigned char *smem, const C2V
         *pe = e;                                              // waits for the commit
         dl += on ? e - eold : 0.0;                            // eEnd - eStart from per-neighbour differences
         if (TRACE) { sl += on ? eold : 0.0; el += on ? e : 0.0; }
-        pxy += SS * L; pz += SS * L; pq += SS * L; pi += SS * L; pe += L;
+        pxy += SS * TL::XROW; pz += SS * TL::XROW; pq += SS * L; pi += SS * L; pe += L;
     }
 }
 
@@ -586,8 +598,8 @@ __device__ __forceinline__ void c2_evaluate_slots(const unsigned char *smem, con
 #pragma unroll
         for (int b = 0; b < SS; b++) {
             const int p = (k * SS + b) * L + tl;
-            const double2 xy = v.xy[p];
-            x[b] = xy.x; y[b] = xy.y; z[b] = v.zs[p]; q[b] = TL::qpos(smem, p);
+            const double2 xy = v.xy[TL::xi(p)];
+            x[b] = xy.x; y[b] = xy.y; z[b] = v.zs[TL::xi(p)]; q[b] = TL::qpos(smem, p);
             info[b] = (HAS_EXP || ljw) ? TL::pos_info(smem, p) : 0;
         }
         double e;
@@ -637,7 +649,7 @@ __device__ __forceinline__ double c2_total_energy(const unsigned char *smem, con
             const int p = TL::pos_of(xm, a);
             const int infi = TL::pos_info(smem, p);
             const int row = info_type(infi) * sys.row_stride;
-            const double xi = v.xy[p].x, yi = v.xy[p].y, zi = v.zs[p];
+            const double xi = v.xy[TL::xi(p)].x, yi = v.xy[TL::xi(p)].y, zi = v.zs[TL::xi(p)];
             const double kqi = K_VALUE * TL::qpos(smem, p);
 #pragma unroll
             for (int k = 0; k < M; k++) {
@@ -651,7 +663,7 @@ __device__ __forceinline__ double c2_total_energy(const unsigned char *smem, con
                         double2 ab = make_double2(0.0, 0.0);
                         if (HAS_EXP) ab = *(const double2 *)(tab_ab + row + cj);
                         // an empty site slot of a shorter particle sits far away with a zero charge and the all-zero column
-                        e[k] = pair_accumulate<HAS_EXP ? 2 : 1>(e[k], v.xy[pj].x - xi, v.xy[pj].y - yi, v.zs[pj] - zi, 0.0, kqi * TL::qpos(smem, pj), cd, ab);
+                        e[k] = pair_accumulate<HAS_EXP ? 2 : 1>(e[k], v.xy[TL::xi(pj)].x - xi, v.xy[TL::xi(pj)].y - yi, v.zs[TL::xi(pj)] - zi, 0.0, kqi * TL::qpos(smem, pj), cd, ab);
                     }
                 }
             }
@@ -669,10 +681,11 @@ __device__ __forceinline__ double c2_total_energy(const unsigned char *smem, con
 template <int L, int M, int SS>
 __device__ __forceinline__ void c2_sites_to_global(const C2View &v, double *dst, const DevSystem &sys, int tl)
 {
+    using TL = C2Tables<L, M, SS>;
 #pragma unroll
     for (int j = 0; j < M * SS; j++) {
         const int p = j * L + tl, i = sys.pos_site[p];
-        if (i >= 0) { dst[3 * i] = v.xy[p].x; dst[3 * i + 1] = v.xy[p].y; dst[3 * i + 2] = v.zs[p]; }
+        if (i >= 0) { dst[3 * i] = v.xy[TL::xi(p)].x; dst[3 * i + 1] = v.xy[TL::xi(p)].y; dst[3 * i + 2] = v.zs[TL::xi(p)]; }
     }
 }
 
@@ -693,11 +706,12 @@ __device__ __noinline__ void c2_total_round(const unsigned char *smem, const C2V
 template <int L, int M, int SS>
 __device__ __forceinline__ void c2_sites_from_global(const C2View &v, const double *src, const DevSystem &sys, int tl)
 {
+    using TL = C2Tables<L, M, SS>;
 #pragma unroll
     for (int j = 0; j < M * SS; j++) {
         const int p = j * L + tl, i = sys.pos_site[p];
-        v.xy[p] = i >= 0 ? make_double2(src[3 * i], src[3 * i + 1]) : make_double2(FAR_AWAY, FAR_AWAY);
-        v.zs[p] = i >= 0 ? src[3 * i + 2] : FAR_AWAY;
+        v.xy[TL::xi(p)] = i >= 0 ? make_double2(src[3 * i], src[3 * i + 1]) : make_double2(FAR_AWAY, FAR_AWAY);
+        v.zs[TL::xi(p)] = i >= 0 ? src[3 * i + 2] : FAR_AWAY;
     }
 }
 
@@ -711,32 +725,12 @@ struct C2Pick {                      // the S-stream part of a move starting at 
 
 constexpr int C2_CTRL_WARPS = 3;
 
-// Which warp plays which role.  Warp w runs on SM sub-partition w % 4.  TR_C2_ROLEMAP 0: warps 0, 1, 2 = C1, C2, C3 (one control
-// warp on each of three sub-partitions); 1: warps 0, 1, 4 = C1, C2, C3 (C1 and C3 share sub-partition 0 with one energy warp).
-#ifndef TR_C2_ROLEMAP
-#define TR_C2_ROLEMAP 0
-#endif
+// Warp w runs on SM sub-partition w % 4: warps 0, 1, 2 = C1, C2, C3 (one control warp on each of three sub-partitions), the
+// rest are energy warps.  (Measured alternatives, (H2O)20: C1 and C3 together on sub-partition 0: -17 %; all three control warps
+// on sub-partition 0: -13 %; the same with six energy warps, two per remaining sub-partition: -18 %.)
 enum { C2_ROLE_C1 = 0, C2_ROLE_C2 = 1, C2_ROLE_C3 = 2, C2_ROLE_E = 3 };
-__device__ __forceinline__ int c2_role(int warp)
-{
-#if TR_C2_ROLEMAP == 1
-    return warp == 0 ? C2_ROLE_C1 : warp == 1 ? C2_ROLE_C2 : warp == 4 ? C2_ROLE_C3 : C2_ROLE_E;
-#elif TR_C2_ROLEMAP == 2
-    return warp == 0 ? C2_ROLE_C1 : warp == 4 ? C2_ROLE_C2 : warp == 8 ? C2_ROLE_C3 : C2_ROLE_E;
-#else
-    return warp < C2_CTRL_WARPS ? warp : C2_ROLE_E;
-#endif
-}
-__device__ __forceinline__ int c2_energy_index(int warp)
-{
-#if TR_C2_ROLEMAP == 1
-    return warp < 4 ? warp - 2 : warp - 3;          // warps 2, 3, 5, 6, 7 ... -> 0, 1, 2, 3, 4 ...
-#elif TR_C2_ROLEMAP == 2
-    return warp < 4 ? warp - 1 : warp < 8 ? warp - 2 : warp - 3;      // warps 1, 2, 3, 5, 6, 7, 9 ... -> 0 .. 6 ...
-#else
-    return warp - C2_CTRL_WARPS;
-#endif
-}
+__device__ __forceinline__ int c2_role(int warp) { return warp < C2_CTRL_WARPS ? warp : C2_ROLE_E; }
+__device__ __forceinline__ int c2_energy_index(int warp) { return warp - C2_CTRL_WARPS; }
 
 #ifndef TR_CREW2_MINB
 #define TR_CREW2_MINB 1
@@ -1279,8 +1273,8 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             if constexpr (TL::WIDE) {
 #pragma unroll
                 for (int j = 0; j < WN; j++) {
-                    const double2 xy = v.xy[j * L + tl];
-                    wx[j] = xy.x; wy[j] = xy.y; wz[j] = v.zs[j * L + tl];
+                    const double2 xy = v.xy[j * TL::XROW + tl];
+                    wx[j] = xy.x; wy[j] = xy.y; wz[j] = v.zs[j * TL::XROW + tl];
                 }
             }
             if (moving) {
