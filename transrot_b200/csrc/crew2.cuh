@@ -72,13 +72,18 @@ constexpr int C2_BAR_PLAN = 2, C2_BAR_RES = 4, C2_BAR_PLAN_B = 6;
 #ifndef TR_C2_LAG
 #define TR_C2_LAG 1800
 #endif
-__device__ __forceinline__ int c2_group(int warp) { return TR_C2_LAG > 0 ? (warp >> 2) & 1 : 0; }
+// which of the two energy warps of a sub-partition leads: 1 = warps 4..7 are group A, warps 3, 8, 9 lag (+ 0.9 % over 0)
+#ifndef TR_C2_GROUP_SWAP
+#define TR_C2_GROUP_SWAP 1
+#endif
+__host__ __device__ constexpr int c2_group(int warp) { return TR_C2_LAG > 0 ? (((warp >> 2) & 1) ^ TR_C2_GROUP_SWAP) : 0; }
+constexpr int C2_STAMP_WARP = TR_C2_GROUP_SWAP ? 4 : 3;          // the first energy warp of group A
 // threads that meet at a group's plan barrier: the three control warps + the group's energy warps (warps 3 .. NW-1 by role map 0)
 template <int NW>
 __host__ __device__ constexpr int c2_plan_threads(int group)
 {
     int n = 3;
-    for (int w = 3; w < NW; w++) n += (TR_C2_LAG > 0 ? ((w >> 2) & 1) : 0) == group ? 1 : 0;
+    for (int w = 3; w < NW; w++) n += c2_group(w) == group ? 1 : 0;
     return 32 * n;
 }
 template <int NW>
@@ -1221,7 +1226,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
             if (r > 0) c2_bar_sync(grp ? C2_BAR_PLAN_B + (r & 1) : C2_BAR_PLAN + (r & 1), c2_plan_threads<NW>(grp));      // plan r is posted
             if (TL::alive(smem, r) == 0) break;
             if (TR_C2_LAG > 0) {
-                if (warp == C2_CTRL_WARPS) {
+                if (warp == C2_STAMP_WARP) {
                     if (lane == 0) *TL::stamp(smem, r) = ((unsigned long long)(unsigned)r << 32) | (unsigned)clock();
                 } else if (grp) {
                     unsigned long long st;
