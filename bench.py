@@ -36,8 +36,13 @@ import numpy as np  # noqa: E402
 METRIC = "MC move attempts/sec"
 UNIT = "moves/s"
 FLOPS_PER_PAIR = 19.0          # A = 0 for every shipped species
-CHAINS_PER_GPU = 4096
-SWEEP_SEEDS = 64               # config #3: 8 sawtooth peaks x 8 magwalk probabilities x 64 seeds = 4096 chains
+# Chains per GPU.  BASELINE.json fixes 4096 for (H2O)20 (and the shipped sample is run the same way); for the other
+# configurations the count is a whole number of waves of the kernel the library picks on a 148-SM B200 - a partial last wave
+# only measures idle SMs ((NH4Cl)32: 4096 chains = 1.73 waves of 16 chains per SM: 594 M moves/s; 4736 = 2 waves: 645):
+#   nh4cl32: 2 waves x 148 SMs x 16 chains = 4736 = 64 parameter sets x 74 seeds;  mixed64: 2 x 148 x 12 = 3552;
+#   h2o256: 2 x 148 x 3 = 888.
+CHAINS_PER_GPU = {"sample8": 4096, "h2o20": 4096, "nh4cl32": 4736, "mixed64": 3552, "h2o256": 888}
+SWEEP_SEEDS = 74               # config #3: 8 sawtooth peaks x 8 magwalk probabilities x 74 seeds = 4736 chains
 
 
 def parse_args():
@@ -77,7 +82,7 @@ def load_problem(args):
 
 
 def chains_per_gpu(args):
-    return args.chains_per_gpu or (CHAINS_PER_GPU if args.workload != "h2o256" else 6 * 148)
+    return args.chains_per_gpu or CHAINS_PER_GPU[args.workload]
 
 
 def sched_index(args, global_chain: np.ndarray, n_sets: int) -> np.ndarray:

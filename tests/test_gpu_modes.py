@@ -314,6 +314,45 @@ def test_error_convention_through_the_abi(dbase, sample_cfg):
         Engine(99)
 
 
+def test_asymmetric_pair_table_keeps_off_the_pair_cache(engine, dbase, sample_cfg):
+    """The C ABI accepts a pair table with [t1][t2] != [t2][t1] (the reference never builds one).  The kernels that keep one cached
+    energy per particle pair would then return whichever orientation was evaluated last: the automatic choice falls back to the
+    kernels that evaluate eStart and eEnd afresh (decisions still equal to the oracle, which walks the same table), and forcing a
+    pair-cache kernel is an error."""
+    import dataclasses
+
+    from transrot_b200 import TransRotError
+    from transrot_b200.engine import TR_KERNEL_CREW2
+
+    cfg = workload_config(sample_cfg, "h2o20", movePerPt=400, ptsPerTooth=3, numTeeth=1)
+    system = system_from_config(dbase, cfg)
+    table = system.pair_table.copy()
+    assert table.shape[0] >= 2
+    table[0, 1, 2] = 3.0 * table[1, 0, 2] + 1.0                  # C of (type 0 moved, type 1 other) only
+    skewed = dataclasses.replace(system, pair_table=table)
+    n_moves = 1200
+    engine.set_system(skewed)
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=n_moves)
+    try:
+        engine.init_chains_seeded([1000, 1001], cfg.spaceLen, cfg.maxPropFailures)
+        assert "crew2" not in engine.kernel_name() and "pair cache" not in engine.kernel_name()
+        engine.run(n_moves)
+        engine.synchronize()
+        tr = engine.trace()
+        for i, seed in enumerate([1000, 1001]):
+            sp = oracle_start(dbase, cfg, seed, pair_table=table)
+            res = sp.sawtooth_anneal(sp.calc_energy(), trace_cap=n_moves)
+            first, err_rel, err_cond = compare_traces(tr[i], res.trace, res.trace_abs)
+            assert first == -1 and err_cond <= 1e-12
+        engine.set_kernel(TR_KERNEL_CREW2)
+        with pytest.raises(TransRotError, match="not symmetric"):
+            engine.init_chains_seeded([1000], cfg.spaceLen, cfg.maxPropFailures)
+    finally:
+        engine.set_kernel(TR_KERNEL_AUTO)
+        engine.set_options(trace_moves=0)
+
+
 @pytest.mark.parametrize("tpc", [0, 16])
 def test_degenerate_schedules(engine, dbase, sample_cfg, tpc):
     """Points per Tooth = 1 makes delT = t / 0 = Infinity (and 0 / 0 = NaN in the finale, where every uphill move is

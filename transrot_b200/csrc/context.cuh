@@ -66,6 +66,7 @@ struct tr_ctx {
 
     // system
     bool have_system = false;
+    bool pair_table_symmetric = true;   // {A,B,C,D}[t1][t2] == [t2][t1] bit for bit (the reference always builds it so: Space.java:346-366)
     tr::DevSystem sys{};
     tr::DevBuf<int> d_mol_off, d_site_info, d_moveable, d_site_ghost;
     tr::DevBuf<double> d_site_q, d_mol_radius, d_site_def, d_site_mass;

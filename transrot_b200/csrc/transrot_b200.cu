@@ -1,6 +1,7 @@
 // C ABI of the B200 annealing backend (include/transrot_b200.h): context, device buffers,
 // kernel dispatch.  No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -251,7 +252,9 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
     ctx->use_crew = ctx->threads_per_chain == 0 && v.W == 1 && ctx->kernel_choice != TR_KERNEL_TEAM &&
                     (v.L == 16 || ctx->kernel_choice == TR_KERNEL_CREW);
     // the particle-major kernel with the pair-energy cache takes over wherever it has a variant (crew2.cuh)
-    ctx->use_crew2 = ctx->threads_per_chain == 0 && (ctx->kernel_choice == TR_KERNEL_CREW2 || (ctx->kernel_choice == TR_KERNEL_AUTO && TR_CREW2_AUTO_BIG) ||
+    NEED(ctx, ctx->pair_table_symmetric || (ctx->kernel_choice != TR_KERNEL_CREW2 && ctx->kernel_choice != TR_KERNEL_TEAM_PC),
+         "Error: the pair table is not symmetric; the kernels with a pair-energy cache (TR_KERNEL_CREW2, TR_KERNEL_TEAM_PC) need a symmetric one");
+    ctx->use_crew2 = ctx->pair_table_symmetric && ctx->threads_per_chain == 0 && (ctx->kernel_choice == TR_KERNEL_CREW2 || (ctx->kernel_choice == TR_KERNEL_AUTO && TR_CREW2_AUTO_BIG) ||
                                                       (ctx->kernel_choice == TR_KERNEL_AUTO && ctx->sys.n_mol <= TR_CREW2_SMALL_MOL)) &&
                      crew2_pick(ctx, max_mol_sites_of(ctx), &ctx->crew2);
     NEED(ctx, ctx->use_crew2 || ctx->kernel_choice != TR_KERNEL_CREW2, "Error: no crew2 kernel variant for this system (%d particles, %d sites in the largest)",
@@ -261,7 +264,8 @@ int alloc_chain_buffers(tr_ctx *ctx, long long n_chains, long long first_chain)
     // (594 vs 554 M moves/s) and (H2O)256 as 3 + 3 (144 vs 135); with eight (the mixed 64-particle cluster as 5 + 3: 409 vs 550)
     // the wider evaluation costs more registers than the halved arithmetic returns.  tr_set_kernel overrides.
     ctx->use_team_pc = false;
-    if (!ctx->use_crew2 && ctx->threads_per_chain == 0 && (ctx->kernel_choice == TR_KERNEL_TEAM_PC || ctx->kernel_choice == TR_KERNEL_AUTO) &&
+    if (!ctx->use_crew2 && ctx->pair_table_symmetric && ctx->threads_per_chain == 0 &&
+        (ctx->kernel_choice == TR_KERNEL_TEAM_PC || ctx->kernel_choice == TR_KERNEL_AUTO) &&
         ctx->sys.n_mol > TR_CREW2_SMALL_MOL && team_pc_pick(ctx, &ctx->team_pc))
         ctx->use_team_pc = ctx->kernel_choice == TR_KERNEL_TEAM_PC || ctx->team_pc.N0 + ctx->team_pc.N1 <= TR_TEAM_PC_AUTO_SLOTS;
     NEED(ctx, ctx->use_team_pc || ctx->kernel_choice != TR_KERNEL_TEAM_PC, "Error: no pair-cache team kernel variant for this system (%d particles, %d sites in the largest)",
@@ -486,6 +490,13 @@ extern "C" int tr_set_system(tr_ctx *ctx, const tr_system *s)
             const double2 v = cd[(size_t)t1 * s->n_types + t2], w = cd[(size_t)t2 * s->n_types + t1];
             if (!(v.x == 0.0) || !(v.y == 0.0) || !(w.x == 0.0) || !(w.y == 0.0) || has_exp) type_lj[(size_t)t1] = 1;
         }
+    // the kernels with a pair-energy cache keep ONE energy per particle pair whichever of the two moved last: that is the
+    // reference's value only when the table is symmetric (it always is when setupPairVals built it; NaN entries compare by bits)
+    ctx->pair_table_symmetric = true;
+    for (int t1 = 0; t1 < s->n_types; t1++)
+        for (int t2 = 0; t2 < t1; t2++)
+            if (memcmp(&s->pair_abcd[4 * ((size_t)t1 * s->n_types + t2)], &s->pair_abcd[4 * ((size_t)t2 * s->n_types + t1)], 4 * sizeof(double)) != 0)
+                ctx->pair_table_symmetric = false;
     ctx->h_site_lj.assign((size_t)s->n_sites, 0);
     for (int i = 0; i < s->n_sites; i++) {
         ctx->h_site_lj[(size_t)i] = type_lj[(size_t)s->site_type[i]];
