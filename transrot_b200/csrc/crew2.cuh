@@ -50,12 +50,12 @@ __device__ __forceinline__ long long c2_clock() { long long t; asm volatile("mov
 // block-wide barrier per round:
 //   plan barrier p (ids 2, 3; parity of the round the plan is for): control warps ARRIVE after writing the plan, energy warps WAIT.
 //   result barrier p (ids 4, 5; parity of the round): energy warps ARRIVE after posting results, control warps WAIT.
-// So a control warp never blocks on posting a plan and an energy warp never blocks on posting its results: an energy warp starts
-// round r + 1 as soon as every energy warp has finished round r (the barrier counts all of them) and the control warps have
-// posted plan r + 1, which they do during round r from the results of round r - 1.  The energy warps of a block therefore still
-// advance round by round together: a round lasts as long as its slowest energy warp.  That is harmless when every move costs
-// the same ((H2O)20: 7 % of an energy warp's time is spent waiting here) and is what makes the whole-warp variants lose against
-// the team kernels on mixed clusters ((NH4Cl)32: a 5-site move next to 1-site moves; 33 % of all samples wait at the plan barrier).
+// So a control warp never blocks on posting a plan and an energy warp never blocks on posting its results.  With one plan
+// barrier per GROUP of energy warps (the whole-warp variants: too many warps for the 16 barrier ids) the warps of a group still
+// advance round by round together - a round lasts as long as its slowest energy warp, which is what makes those variants lose on
+// mixed clusters ((NH4Cl)32: a 5-site move next to 1-site moves; 33 % of all samples wait at the plan barrier).  With one plan
+// barrier per energy WARP (TR_C2_PER_WARP, up to 10 energy warps) a warp waits for the control warps only; it can run up to a
+// round ahead of the slowest one, because plan r + 1 is built from the results of round r - 1.
 __device__ __forceinline__ void c2_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void c2_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 constexpr int C2_BAR_PLAN = 2, C2_BAR_RES = 4, C2_BAR_PLAN_B = 6;
