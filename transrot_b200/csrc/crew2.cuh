@@ -89,11 +89,13 @@ __host__ __device__ constexpr int c2_plan_threads(int group)
 }
 // TR_C2_PER_WARP: one plan barrier per energy warp (ids 6 ..; the three control warps arrive, that warp waits) instead of one per
 // group, so an energy warp waits for the control warps only, never for another energy warp (+ 1.8 % on (H2O)20, + 1.6 % on the
-// sample cluster).  One id per warp is enough, without a parity: between two arrivals of the control warps at warp w's barrier
-// lies their wait for the results of the round in between, which warp w posts one instruction before it waits at its barrier.
-// Blocks with more than 10 energy warps (the whole-warp variants) run out of barrier ids and keep the two group barriers.
+// sample cluster).  One id per warp, without a parity: between two arrivals of the control warps at warp w's barrier lies their
+// wait for the results of the round in between, which warp w posts one instruction before it waits at its barrier.
+// OFF BY DEFAULT: together with the two-group lag (TR_C2_LAG > 0) a launch deadlocked about once in 140 launches
+// (tools/stress_hang.py; either feature alone ran 500 launches clean).  The cause was not found; the group barriers are kept.
+// Blocks with more than 10 energy warps (the whole-warp variants) would run out of barrier ids anyway.
 #ifndef TR_C2_PER_WARP
-#define TR_C2_PER_WARP 1
+#define TR_C2_PER_WARP 0
 #endif
 constexpr int C2_BAR_PLAN_W = 6;
 template <int NW>
