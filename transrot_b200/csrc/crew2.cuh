@@ -87,13 +87,15 @@ __host__ __device__ constexpr int c2_plan_threads(int group)
     for (int w = 3; w < NW; w++) n += c2_group(w) == group ? 1 : 0;
     return 32 * n;
 }
-// TR_C2_PER_WARP: one plan barrier per energy warp (ids 6 ..; the three control warps arrive, that warp waits) instead of one per
-// group, so an energy warp waits for the control warps only, never for another energy warp (+ 1.8 % on (H2O)20, + 1.6 % on the
-// sample cluster).  One id per warp, without a parity: between two arrivals of the control warps at warp w's barrier lies their
-// wait for the results of the round in between, which warp w posts one instruction before it waits at its barrier.
-// OFF BY DEFAULT: together with the two-group lag (TR_C2_LAG > 0) a launch deadlocked about once in 140 launches
-// (tools/stress_hang.py; either feature alone ran 500 launches clean).  The cause was not found; the group barriers are kept.
-// Blocks with more than 10 energy warps (the whole-warp variants) would run out of barrier ids anyway.
+// TR_C2_PER_WARP (experiment, OFF): one named plan barrier per energy warp (ids 6 ..; the three control warps arrive, that warp
+// waits) instead of one per group, so that an energy warp waits for the control warps only (+ 1.8 % on (H2O)20).  NOT SAFE:
+// there are not enough barrier ids for two per warp (one per round parity), and with one per warp nothing but the length of a
+// control iteration keeps the control warps' next arrival behind the warp's wait for the previous one.  In the short rounds at
+// the end of a launch the arrival can overtake the wait, the barrier then counts arrivals of two phases into one, and the warp
+// waits forever: about one launch in 140 deadlocked (tools/stress_hang.py).  The group barriers alternate by round parity and
+// are safe by construction (an arrival for plan r + 2 follows the results of round r, hence the wait for plan r).  A safe
+// per-warp hand-off with two mbarrier objects per warp ran 4 000 launches clean but measured no gain over the group barriers
+// (1.672 vs 1.67 G), so it was not kept.
 #ifndef TR_C2_PER_WARP
 #define TR_C2_PER_WARP 0
 #endif
