@@ -314,6 +314,51 @@ def test_error_convention_through_the_abi(dbase, sample_cfg):
         Engine(99)
 
 
+def _untemper(y: int) -> int:
+    """Inverse of the MT19937 tempering (MersenneTwister.next, commons-math3)."""
+    y ^= y >> 18
+    y ^= (y << 15) & 0xEFC60000
+    t = y
+    for _ in range(5):
+        t = y ^ ((t << 7) & 0x9D2C5680)
+    y = t & 0xFFFFFFFF
+    t = y
+    for _ in range(3):
+        t = y ^ (t >> 11)
+    return t & 0xFFFFFFFF
+
+
+def test_abandoned_chain_is_an_error_of_the_run(engine, dbase, sample_cfg):
+    """CHAIN_ABORT_RNG surfaces as TR_ERNG.  The warp-specialised kernels look a fixed number of words ahead for
+    Molecule.java:68's nextInt(3) rejection loop; an R stream whose next 624 outputs are all 0xffffffff (every try rejected:
+    bits = 2^31 - 1) cannot be served from that window, the chain is abandoned (done = 2) and tr_get_summary reports it instead
+    of returning a result that silently differs from the reference (which would keep drawing until the block regenerates)."""
+    from transrot_b200 import TransRotError
+
+    assert _untemper(0) == 0
+    cfg = workload_config(sample_cfg, "h2o20", movePerPt=300, ptsPerTooth=3, numTeeth=1)
+    engine.set_system(system_from_config(dbase, cfg))
+    engine.set_schedules(cfg)
+    engine.set_options(trace_moves=0)
+    engine.init_chains_seeded([1000, 1001], cfg.spaceLen, cfg.maxPropFailures)
+    assert "crew2" in engine.kernel_name()
+    sites, _ = engine.sites()
+    states = engine.rng_state().copy()
+    space_len = float(engine.summary()["space_len"][0])
+    assert float(engine.summary()["space_len"][1]) == space_len
+    stuck = states.copy()
+    stuck[1, 2, :624] = _untemper(0xFFFFFFFF)          # stream R of chain 1
+    stuck[1, 2, 624] = 0
+    engine.init_chains_explicit(2, sites, space_len, mt_state=stuck)
+    engine.run(0)
+    with pytest.raises(TransRotError, match="abandoned"):
+        engine.summary()
+    # the same start with the untouched streams runs to the end
+    engine.init_chains_explicit(2, sites, space_len, mt_state=states)
+    engine.run(0)
+    assert (engine.summary()["done"] == 1).all()
+
+
 def test_asymmetric_pair_table_keeps_off_the_pair_cache(engine, dbase, sample_cfg):
     """The C ABI accepts a pair table with [t1][t2] != [t2][t1] (the reference never builds one).  The kernels that keep one cached
     energy per particle pair would then return whichever orientation was evaluated last: the automatic choice falls back to the
