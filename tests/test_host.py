@@ -163,3 +163,22 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "oracle" not in text.replace("the oracle", "").replace("CPU oracle", "").lower() or f == "host.py", f
+
+
+def test_bench_workload_sizes_are_whole_sweeps():
+    """bench.py's chain counts: config #3 is 64 parameter sets x SWEEP_SEEDS seeds per GPU, every set equally often on every GPU
+    (the set index depends on the GLOBAL chain id, so the sweep is the same at 1, 2, 4 and 8 GPUs)."""
+    import importlib.util
+    import os
+
+    import numpy as np
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.CHAINS_PER_GPU["nh4cl32"] == 64 * bench.SWEEP_SEEDS
+    assert bench.CHAINS_PER_GPU["h2o20"] == 4096                      # BASELINE.json configs[1]
+    for rank in range(8):
+        first = rank * bench.CHAINS_PER_GPU["nh4cl32"]
+        idx = bench.sched_index(None, np.arange(first, first + bench.CHAINS_PER_GPU["nh4cl32"]), 64)
+        assert np.array_equal(np.bincount(idx, minlength=64), np.full(64, bench.SWEEP_SEEDS))
