@@ -768,6 +768,7 @@ crew2_kernel(const __grid_constant__ KParams P, const int C)
     constexpr int NW = C2_CTRL_WARPS + EW;
     constexpr int NT = 32 * NW;
     static_assert(EW * TPW <= 32, "one control lane per chain");
+    static_assert(TR_C2_LAG == 0 || C2_STAMP_WARP < NW, "the lagging group follows the time stamps of an energy warp that exists");
     static_assert(SS <= L, "one lane per site of the moved particle");
     extern __shared__ __align__(16) unsigned char smem[];
     const DevSystem &sys = P.sys;
