@@ -92,6 +92,17 @@ public final class TransRotB200 implements AutoCloseable {
     private static final MethodHandle TR_MULTI_SYNCHRONIZE = handle("tr_multi_synchronize", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle TR_GATHER_MINIMA = handle("tr_gather_minima", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle TR_GATHER_MIN_STRUCTURES = handle("tr_gather_min_structures", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    // the rest of the header, bound for completeness (tools, experiments and parity probes; sawtoothAnneal does not need them)
+    static final MethodHandle TR_SET_STREAM = handle("tr_set_stream", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle TR_SET_KERNEL = handle("tr_set_kernel", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT));
+    static final MethodHandle TR_LAUNCH_COUNT = handle("tr_launch_count", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle TR_PACK_MIN_STRUCTURES = handle("tr_pack_min_structures", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS));
+    static final MethodHandle TR_MULTI_SIZE = handle("tr_multi_size", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle TR_MULTI_CHAIN_RANGE = handle("tr_multi_chain_range", FunctionDescriptor.ofVoid(JAVA_INT, JAVA_INT, JAVA_LONG, ADDRESS, ADDRESS));
+    static final MethodHandle TR_MULTI_LAST_RUN_MS = handle("tr_multi_last_run_ms", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle TR_DELTA_ENERGY = handle("tr_delta_energy", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle TR_RNG_WORDS = handle("tr_rng_words", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS));
+    static final MethodHandle TR_MEASURE_FP64_PEAK = handle("tr_measure_fp64_peak", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
 
     // ------------------------------------------------------------------------------------------ struct layouts (include/transrot_b200.h)
 

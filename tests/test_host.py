@@ -182,3 +182,76 @@ def test_bench_workload_sizes_are_whole_sweeps():
         first = rank * bench.CHAINS_PER_GPU["nh4cl32"]
         idx = bench.sched_index(None, np.arange(first, first + bench.CHAINS_PER_GPU["nh4cl32"]), 64)
         assert np.array_equal(np.bincount(idx, minlength=64), np.full(64, bench.SWEEP_SEEDS))
+
+
+def test_java_struct_layouts_match_the_header():
+    """java/main/TransRotB200.java cannot be compiled here (no JDK), so its Panama StructLayouts are checked as text: same field
+    names, order and types as the structs of include/transrot_b200.h, every member naturally aligned without implicit padding
+    (MemoryLayout.structLayout adds none and rejects misaligned members), same total size as the C compiler's layout."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "transrot_b200.h")).read()
+    java = open(os.path.join(root, "java", "main", "TransRotB200.java")).read()
+    c_size = {"int32_t": 4, "int8_t": 1, "double": 8, "int64_t": 8, "uint32_t": 4, "ptr": 8}
+    j_size = {"JAVA_INT": 4, "JAVA_BYTE": 1, "JAVA_DOUBLE": 8, "JAVA_LONG": 8, "ADDRESS": 8}
+    j_of_c = {"int32_t": "JAVA_INT", "int8_t": "JAVA_BYTE", "double": "JAVA_DOUBLE", "int64_t": "JAVA_LONG", "ptr": "ADDRESS"}
+    for cname, jname in (("tr_system", "TR_SYSTEM"), ("tr_schedule", "TR_SCHEDULE"), ("tr_point_rec", "TR_POINT_REC"),
+                         ("tr_trace_rec", "TR_TRACE_REC"), ("tr_chain_summary", "TR_CHAIN_SUMMARY"), ("tr_minimum", "TR_MINIMUM")):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        c_fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(?:const\s+)?(\w+)\s*(\*?)\s*(\w+)$", decl)
+            assert m, (cname, decl)
+            c_fields.append(("ptr" if m.group(2) else m.group(1), m.group(3)))
+        jbody = re.search(r"StructLayout %s = MemoryLayout\.structLayout\((.*?)\);" % jname, java, re.S).group(1)
+        j_fields = re.findall(r"(JAVA_INT|JAVA_BYTE|JAVA_DOUBLE|JAVA_LONG|ADDRESS)\.withName\(\"(\w+)\"\)", jbody)
+        assert "paddingLayout" not in jbody
+        assert [n for _, n in j_fields] == [n for _, n in c_fields], cname
+        assert [t for t, _ in j_fields] == [j_of_c[t] for t, _ in c_fields], cname
+        off, biggest = 0, 1
+        for t, n in j_fields:
+            assert off % j_size[t] == 0, f"{jname}.{n} would need implicit padding at offset {off}"
+            off += j_size[t]
+            biggest = max(biggest, j_size[t])
+        assert off % biggest == 0, f"{jname}: C pads the tail, the Java layout does not"
+        assert off == sum(c_size[t] for t, _ in c_fields)
+
+
+def test_java_binding_declares_every_function_of_the_header():
+    """Every prototype of include/transrot_b200.h has a downcall handle in java/main/TransRotB200.java with the same arity and the
+    Panama value layouts its C types map to (checked as text: the image has no JDK)."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "transrot_b200.h")).read(), flags=re.S)
+    java = open(os.path.join(root, "java", "main", "TransRotB200.java")).read()
+    scalar = {"int": "JAVA_INT", "int32_t": "JAVA_INT", "int64_t": "JAVA_LONG", "long long": "JAVA_LONG", "double": "JAVA_DOUBLE", "float": "JAVA_FLOAT"}
+
+    def layout(decl, is_return=False):
+        decl = decl.replace("const", " ").strip()
+        if "*" in decl:
+            return "ADDRESS"
+        toks = decl.split()
+        ty = " ".join(toks if is_return or len(toks) == 1 else toks[:-1])
+        return "VOID" if ty == "void" else scalar[ty]
+
+    protos = re.findall(r"^\s*((?:const\s+)?\w+(?:\s+\w+)*\s*\*?)\s*(tr_\w+)\s*\(([^;{]*?)\)\s*;", header, re.M | re.S)
+    assert len(protos) >= 47
+    handles = {}
+    for m in re.finditer(r'handle\("(tr_\w+)",\s*FunctionDescriptor\.(of|ofVoid)\(([^;]*?)\)\);', java, re.S):
+        handles[m.group(1)] = (m.group(2), [a.strip() for a in m.group(3).replace("\n", " ").split(",") if a.strip()])
+    for ret, name, args in protos:
+        params = [] if args.strip() in ("", "void") else [layout(a) for a in args.replace("\n", " ").split(",")]
+        r = layout(ret, is_return=True)
+        assert name in handles, f"{name} has no downcall handle"
+        kind, jargs = handles[name]
+        assert (kind == "ofVoid") == (r == "VOID"), name
+        assert jargs == ([] if r == "VOID" else [r]) + params, (name, jargs, params)
+    assert set(handles) == {p[1] for p in protos}
